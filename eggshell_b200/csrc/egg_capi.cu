@@ -1,0 +1,410 @@
+// C ABI of libeggshell_b200.so (declared in include/egg_cuda.h).  Host-side plumbing only:
+// device allocation, AoS<->SoA staging, kernel sequencing for Ensemble::Step
+// (/root/reference/eggshell/ensembles.cc:390-427).  There is no CPU fallback: without a CUDA
+// device every entry point fails with EGG_ERR_NO_DEVICE.
+#include "../../include/egg_cuda.h"
+#include "egg_internal.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+void egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes);
+size_t egg_dense_scratch_bytes(const EggDev& d);
+
+static thread_local std::string g_err;
+static void set_err(const char* what, cudaError_t e) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  g_err = buf;
+}
+#define CK(call)                                \
+  do {                                          \
+    cudaError_t e__ = (call);                   \
+    if (e__ != cudaSuccess) {                   \
+      set_err(#call, e__);                      \
+      return EGG_ERR_CUDA;                      \
+    }                                           \
+  } while (0)
+
+struct egg_batch {
+  egg_desc desc;
+  EggDev dev;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  bool initialised = false;
+  std::vector<void*> allocs;
+  long long bytes = 0;
+  long long launches = 0;
+  double* stage = nullptr;        // device staging for AoS <-> SoA conversion
+  size_t stage_bytes = 0;
+  void* dense_scratch = nullptr;
+  size_t dense_scratch_bytes = 0;
+  int device = 0;
+};
+
+template <class T>
+static int dalloc(egg_batch* b, T** p, size_t count) {
+  size_t bytes = count * sizeof(T);
+  if (bytes == 0) bytes = sizeof(T);
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) { set_err("cudaMalloc", e); return EGG_ERR_CUDA; }
+  e = cudaMemsetAsync(q, 0, bytes, b->stream);
+  if (e != cudaSuccess) { set_err("cudaMemset", e); return EGG_ERR_CUDA; }
+  b->allocs.push_back(q);
+  b->bytes += (long long)bytes;
+  *p = (T*)q;
+  return EGG_OK;
+}
+#define DA(ptr, count)                                  \
+  do {                                                  \
+    int r__ = dalloc(b, &(ptr), (size_t)(count));       \
+    if (r__ != EGG_OK) { egg_destroy(b); return r__; }  \
+  } while (0)
+
+extern "C" {
+
+const char* egg_last_error(void) { return g_err.c_str(); }
+const char* egg_version(void) { return "eggshell_b200 0.1 (sm_100a)"; }
+
+int egg_desc_default(egg_desc* d, int n_worlds, int n_bodies, int n_joints) {
+  if (!d) return EGG_ERR_ARG;
+  memset(d, 0, sizeof(*d));
+  d->n_worlds = n_worlds;
+  d->n_bodies = n_bodies;
+  d->n_joints = n_joints;
+  d->max_contacts = 0;
+  d->precision = 64;
+  d->solver = EGG_SOLVER_DENSE_MURTY;   // what the reference ships (ensembles.cc:21)
+  d->k_max = 500;                       // sparse_iterations.cc:19
+  d->tol = 1e-9;                        // constants.h:5
+  d->cfm = 0.01;                        // ensembles.cc:14
+  d->erp = 0.2;                         // ensembles.h:166
+  d->gravity[0] = 0; d->gravity[1] = 0; d->gravity[2] = -9.8;   // constants.h:8
+  d->min_constraint_dist = 1e-6;        // ensembles.cc:15
+  d->quirks = EGG_QUIRKS_REFERENCE;
+  d->cfm_mode = EGG_CFM_AUTO;
+  d->device = 0;
+  d->taps = 0;
+  return EGG_OK;
+}
+
+int egg_create(const egg_desc* dsc, egg_batch** out) {
+  if (!dsc || !out) return EGG_ERR_ARG;
+  *out = nullptr;
+  if (dsc->n_worlds <= 0 || dsc->n_bodies <= 0 || dsc->n_joints < 0 || dsc->n_bodies > 360) { g_err = "bad shape"; return EGG_ERR_ARG; }
+  if (dsc->precision != 64) { g_err = "only FP64 is implemented"; return EGG_ERR_UNSUPPORTED; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_err = "no CUDA device: eggshell_b200 has no CPU fallback";
+    return EGG_ERR_NO_DEVICE;
+  }
+  if (dsc->device < 0 || dsc->device >= ndev) { g_err = "bad device ordinal"; return EGG_ERR_ARG; }
+  CK(cudaSetDevice(dsc->device));
+  egg_batch* b = new egg_batch();
+  b->desc = *dsc;
+  b->device = dsc->device;
+  e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { set_err("cudaStreamCreate", e); delete b; return EGG_ERR_CUDA; }
+  b->own_stream = true;
+
+  EggDev& d = b->dev;
+  memset(&d, 0, sizeof(d));
+  const int W = dsc->n_worlds, n = dsc->n_bodies, nj = dsc->n_joints;
+  d.W = W; d.n = n; d.nj = nj;
+  d.P = n * (n - 1) / 2;
+  // Capacity: 8 ground contacts per body is exact (collision.cc:412-414); pairs emit <= 10 each
+  // (4-gon clipped by 6 half-spaces).  Automatic = 8 n + 4 contacts for ~4 colliding pairs/body.
+  int maxc = dsc->max_contacts > 0 ? dsc->max_contacts : 8 * n + 16 * n;
+  if (maxc > 8 * n + 10 * d.P) maxc = 8 * n + 10 * d.P;
+  if (maxc < 8) maxc = 8;
+  maxc = (maxc + 7) & ~7;
+  d.maxc = maxc;
+  d.nrec = nj + maxc;
+  b->desc.max_contacts = maxc;
+  d.prm.erp = dsc->erp; d.prm.cfm = dsc->cfm; d.prm.tol = dsc->tol; d.prm.min_dist = dsc->min_constraint_dist;
+  for (int k = 0; k < 3; k++) d.prm.g[k] = dsc->gravity[k];
+  d.prm.k_max = dsc->k_max; d.prm.solver = dsc->solver; d.prm.quirks = dsc->quirks; d.prm.cfm_mode = dsc->cfm_mode;
+
+  DA(d.dyn, (size_t)W * EGG_DYN * n);
+  DA(d.stat, (size_t)W * EGG_STAT * n);
+  DA(d.bpar, (size_t)W * EGG_BPAR * n);
+  DA(d.j_i0, (size_t)W * nj);
+  DA(d.j_i1, (size_t)W * nj);
+  DA(d.jc, (size_t)W * 6 * nj);
+  DA(d.c_count, W);
+  DA(d.c_i0, (size_t)W * maxc);
+  DA(d.c_i1, (size_t)W * maxc);
+  DA(d.c_code, (size_t)W * maxc);
+  DA(d.c_geom, (size_t)W * 7 * maxc);
+  if (dsc->taps) {
+    DA(d.pair_code, (size_t)W * d.P);
+    DA(d.pair_cnt, (size_t)W * d.P);
+  }
+  DA(d.rec, (size_t)W * d.nrec * EGG_REC);
+  DA(d.lam, (size_t)W * d.nrec * 3);
+  DA(d.lam_out, (size_t)W * d.nrec * 3);
+  DA(d.row_state, (size_t)W * d.nrec * 3);
+  DA(d.level_start, (size_t)W * (d.nrec + 1));
+  DA(d.n_levels, W);
+  DA(d.status, W);
+  DA(d.stats, (size_t)W * 8);
+  DA(d.resid, W);
+  DA(d.cost0, (size_t)W * 2);
+  b->stage_bytes = (size_t)W * n * 9 * sizeof(double);
+  size_t jb = (size_t)W * (nj > 0 ? nj : 1) * 3 * sizeof(double);
+  if (jb > b->stage_bytes) b->stage_bytes = jb;
+  DA(b->stage, b->stage_bytes / sizeof(double));
+  if (dsc->solver == EGG_SOLVER_DENSE_MURTY) {
+    b->dense_scratch_bytes = egg_dense_scratch_bytes(d);
+    char* p = nullptr;
+    DA(p, b->dense_scratch_bytes);
+    b->dense_scratch = p;
+  }
+  CK(cudaStreamSynchronize(b->stream));
+  *out = b;
+  return EGG_OK;
+}
+
+void egg_destroy(egg_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (void* p : b->allocs) cudaFree(p);
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  delete b;
+}
+
+int egg_set_stream(egg_batch* b, void* cuda_stream) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
+  b->stream = (cudaStream_t)cuda_stream;
+  b->own_stream = false;
+  return EGG_OK;
+}
+
+int egg_sync(egg_batch* b) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaGetLastError());
+  return EGG_OK;
+}
+
+int egg_capacity(const egg_batch* b) { return b ? b->dev.maxc : 0; }
+long long egg_device_bytes(const egg_batch* b) { return b ? b->bytes : 0; }
+long long egg_launch_count(const egg_batch* b) { return b ? b->launches : 0; }
+
+void* egg_host_alloc(long long bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+void egg_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+// Host AoS [W][per_world][comps] -> device SoA component block.
+static int upload(egg_batch* b, const double* host, int per_world, int comps, double* soa, int soa_comps, int comp_off) {
+  size_t bytes = (size_t)b->dev.W * per_world * comps * sizeof(double);
+  if (bytes == 0) return EGG_OK;
+  CK(cudaMemcpyAsync(b->stage, host, bytes, cudaMemcpyHostToDevice, b->stream));
+  egg_launch_pack(b->dev.W, b->stage, per_world, comps, soa, soa_comps, comp_off, b->stream);
+  b->launches++;
+  CK(cudaGetLastError());
+  return EGG_OK;
+}
+static int download(egg_batch* b, double* host, int per_world, int comps, const double* soa, int soa_comps, int comp_off) {
+  size_t bytes = (size_t)b->dev.W * per_world * comps * sizeof(double);
+  if (bytes == 0) return EGG_OK;
+  egg_launch_unpack(b->dev.W, b->stage, per_world, comps, soa, soa_comps, comp_off, b->stream);
+  b->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(host, b->stage, bytes, cudaMemcpyDeviceToHost, b->stream));
+  // the staging buffer is reused by the next call
+  CK(cudaStreamSynchronize(b->stream));
+  return EGG_OK;
+}
+#define RET(x) do { int r__ = (x); if (r__ != EGG_OK) return r__; } while (0)
+
+int egg_set_state(egg_batch* b, const double* p, const double* R, const double* v, const double* w) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const int n = b->dev.n;
+  if (p) RET(upload(b, p, n, 3, b->dev.dyn, EGG_DYN, 0));
+  if (R) RET(upload(b, R, n, 9, b->dev.dyn, EGG_DYN, 3));
+  if (v) RET(upload(b, v, n, 3, b->dev.dyn, EGG_DYN, 12));
+  if (w) RET(upload(b, w, n, 3, b->dev.dyn, EGG_DYN, 15));
+  return EGG_OK;
+}
+
+int egg_set_bodies(egg_batch* b, const double* p, const double* R, const double* v, const double* w,
+                   const double* m, const double* I_body, const double* side) {
+  if (!b || !p || !R || !v || !w || !m || !I_body) return EGG_ERR_ARG;
+  RET(egg_set_state(b, p, R, v, w));
+  const int n = b->dev.n;
+  if (side) RET(upload(b, side, n, 3, b->dev.bpar, EGG_BPAR, 0));
+  else {
+    std::vector<double> s((size_t)b->dev.W * n * 3, 0.3);    // body.h:91
+    RET(upload(b, s.data(), n, 3, b->dev.bpar, EGG_BPAR, 0));
+    CK(cudaStreamSynchronize(b->stream));
+  }
+  RET(upload(b, m, n, 1, b->dev.bpar, EGG_BPAR, 3));
+  RET(upload(b, I_body, n, 9, b->dev.bpar, EGG_BPAR, 4));
+  b->initialised = false;
+  return EGG_OK;
+}
+
+int egg_set_joints(egg_batch* b, const int* i0, const int* i1, const double* c0, const double* c1) {
+  if (!b) return EGG_ERR_ARG;
+  const int nj = b->dev.nj;
+  if (nj == 0) return EGG_OK;
+  if (!i0 || !i1 || !c0 || !c1) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const size_t cnt = (size_t)b->dev.W * nj;
+  for (size_t k = 0; k < cnt; k++) {
+    if (i0[k] < 0 || i0[k] >= b->dev.n || i1[k] < -1 || i1[k] >= b->dev.n) { g_err = "joint body index out of range"; return EGG_ERR_ARG; }
+  }
+  CK(cudaMemcpyAsync(b->dev.j_i0, i0, cnt * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  CK(cudaMemcpyAsync(b->dev.j_i1, i1, cnt * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+  RET(upload(b, c0, nj, 3, b->dev.jc, 6, 0));
+  RET(upload(b, c1, nj, 3, b->dev.jc, 6, 3));
+  b->initialised = false;
+  return EGG_OK;
+}
+
+int egg_set_external(egg_batch* b, const double* f_ext) {
+  if (!b || !f_ext) return EGG_ERR_ARG;
+  if (!b->initialised) { g_err = "egg_set_external must follow egg_init"; return EGG_ERR_STATE; }
+  CK(cudaSetDevice(b->device));
+  return upload(b, f_ext, b->dev.n, 6, b->dev.stat, EGG_STAT, 10);
+}
+
+int egg_init(egg_batch* b) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  egg_launch_init(b->dev, b->stream);
+  b->launches += (b->dev.nj > 0) ? 2 : 1;
+  CK(cudaGetLastError());
+  b->initialised = true;
+  return EGG_OK;
+}
+
+int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
+  if (!b || n_steps < 0 || !(dt > 0)) return EGG_ERR_ARG;
+  if (!b->initialised) { g_err = "egg_step before egg_init"; return EGG_ERR_STATE; }
+  if (integrator != EGG_OPEN_DYNAMICS_ENGINE) {
+    // ensembles.cc:398-405: EXPLICIT_EULER refuses contacts, IMPLICIT_MIDPOINT panics.
+    g_err = "only OPEN_DYNAMICS_ENGINE is supported (as in the reference once contacts exist)";
+    return EGG_ERR_UNSUPPORTED;
+  }
+  const int solver = b->dev.prm.solver;
+  if (solver != EGG_SOLVER_PGS && solver != EGG_SOLVER_DENSE_MURTY) {
+    g_err = "solver not implemented on the device yet";
+    return EGG_ERR_UNSUPPORTED;
+  }
+  CK(cudaSetDevice(b->device));
+  for (int s = 0; s < n_steps; s++) {
+    egg_launch_collide(b->dev, b->stream);
+    egg_launch_assemble(b->dev, dt, b->stream);
+    if (solver == EGG_SOLVER_PGS) egg_launch_solve_pgs(b->dev, dt, b->stream);
+    else egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes);
+    b->launches += 3;
+  }
+  CK(cudaGetLastError());
+  return EGG_OK;
+}
+
+int egg_get_bodies(egg_batch* b, double* p, double* R, double* v, double* w) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const int n = b->dev.n;
+  if (p) RET(download(b, p, n, 3, b->dev.dyn, EGG_DYN, 0));
+  if (R) RET(download(b, R, n, 9, b->dev.dyn, EGG_DYN, 3));
+  if (v) RET(download(b, v, n, 3, b->dev.dyn, EGG_DYN, 12));
+  if (w) RET(download(b, w, n, 3, b->dev.dyn, EGG_DYN, 15));
+  CK(cudaStreamSynchronize(b->stream));
+  return EGG_OK;
+}
+
+int egg_get_contacts(egg_batch* b, int* count, int* i0, int* i1, double* pos, double* nrm,
+                     double* depth, int* code, double* lambda, int* row_state) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const EggDev& d = b->dev;
+  const size_t W = d.W, mc = d.maxc;
+  if (count) CK(cudaMemcpyAsync(count, d.c_count, W * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (i0) CK(cudaMemcpyAsync(i0, d.c_i0, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (i1) CK(cudaMemcpyAsync(i1, d.c_i1, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (code) CK(cudaMemcpyAsync(code, d.c_code, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (lambda) CK(cudaMemcpyAsync(lambda, d.lam_out, W * 3 * d.nrec * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (row_state) CK(cudaMemcpyAsync(row_state, d.row_state, W * 3 * d.nrec * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  if (pos || nrm || depth) {
+    std::vector<double> g(W * 7 * mc);
+    CK(cudaMemcpyAsync(g.data(), d.c_geom, g.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (size_t w = 0; w < W; w++)
+      for (size_t k = 0; k < mc; k++) {
+        const double* gw = g.data() + w * 7 * mc;
+        if (pos) for (int c = 0; c < 3; c++) pos[(w * mc + k) * 3 + c] = gw[c * mc + k];
+        if (nrm) for (int c = 0; c < 3; c++) nrm[(w * mc + k) * 3 + c] = gw[(3 + c) * mc + k];
+        if (depth) depth[w * mc + k] = gw[6 * mc + k];
+      }
+  }
+  return EGG_OK;
+}
+
+int egg_get_pair_hits(egg_batch* b, int* n_hits, int* pi, int* pj, int* code, int* count, int max_pairs) {
+  if (!b || !n_hits) return EGG_ERR_ARG;
+  const EggDev& d = b->dev;
+  if (!d.pair_code) { g_err = "egg_get_pair_hits needs desc.taps = 1"; return EGG_ERR_STATE; }
+  CK(cudaSetDevice(b->device));
+  const size_t W = d.W, P = d.P;
+  std::vector<unsigned char> pc(W * P), pn(W * P);
+  CK(cudaMemcpyAsync(pc.data(), d.pair_code, W * P, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaMemcpyAsync(pn.data(), d.pair_cnt, W * P, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  for (size_t w = 0; w < W; w++) {
+    int h = 0;
+    size_t q = 0;
+    for (int i = 0; i < d.n; i++)
+      for (int j = i + 1; j < d.n; j++, q++) {
+        if (!pc[w * P + q]) continue;
+        if (h < max_pairs) {
+          if (pi) pi[w * max_pairs + h] = i;
+          if (pj) pj[w * max_pairs + h] = j;
+          if (code) code[w * max_pairs + h] = pc[w * P + q];
+          if (count) count[w * max_pairs + h] = pn[w * P + q];
+        }
+        h++;
+      }
+    n_hits[w] = h;
+  }
+  return EGG_OK;
+}
+
+int egg_get_status(egg_batch* b, int* status, int* stats, double* residual) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const size_t W = b->dev.W;
+  if (status) CK(cudaMemcpyAsync(status, b->dev.status, W * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (stats) CK(cudaMemcpyAsync(stats, b->dev.stats, W * 8 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (residual) CK(cudaMemcpyAsync(residual, b->dev.resid, W * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return EGG_OK;
+}
+
+int egg_rollout_costs(egg_batch* b, double* cost_d) {
+  if (!b || !cost_d) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  egg_launch_costs(b->dev, cost_d, b->stream);
+  b->launches++;
+  CK(cudaGetLastError());
+  return EGG_OK;
+}
+
+}  // extern "C"

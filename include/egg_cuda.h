@@ -1,0 +1,157 @@
+/* egg_cuda.h — C ABI of the B200 batched rigid-body step (libeggshell_b200.so).
+ *
+ * The reference (teenylasers/eggshell) has no plugin/FFI: its boundary is the C++ link-time
+ * surface `Ensemble::{Init,Step}` (/root/reference/eggshell/ensembles.h:25-177) driven by
+ * `SimulationInitialization()/SimulationStep()` (/root/reference/eggshell/model.h:8-13).  Each
+ * entry point below names the reference interface it replaces.  The source-compatible C++ mirror
+ * of those headers (include/eggshell/) forwards to this ABI; see INTEGRATION.md.
+ *
+ * Conventions: every pointer is a HOST pointer unless the name ends in _d (device).  Host arrays
+ * are array-of-structs in world-major order: [world][body][k] or [world][joint][k]; matrices are
+ * 3x3 row-major.  All functions return 0 on success or a negative egg_error; nothing aborts the
+ * process and no exception crosses the boundary (the reference's Panic()/_exit(1),
+ * /root/reference/toolkit/error.cc:44-49, becomes a per-world status word).  One host thread
+ * drives one batch; calls on one batch are not thread-safe (same contract as the reference's
+ * single GUI thread, /root/reference/eggshell/eggshell_view.cc:540-554).
+ */
+#ifndef EGG_CUDA_H_
+#define EGG_CUDA_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct egg_batch egg_batch; /* opaque: owns all device memory of W independent worlds */
+
+enum egg_error {
+  EGG_OK = 0,
+  EGG_ERR_ARG = -1,       /* bad argument / descriptor */
+  EGG_ERR_CUDA = -2,      /* a CUDA runtime call failed; see egg_last_error() */
+  EGG_ERR_NO_DEVICE = -3, /* no CUDA device: there is NO CPU fallback */
+  EGG_ERR_STATE = -4,     /* call order violated (e.g. egg_step before egg_init) */
+  EGG_ERR_UNSUPPORTED = -5
+};
+
+/* ensembles.h:45-49 enum Integrator.  Only OPEN_DYNAMICS_ENGINE works with contacts in the
+ * reference (ensembles.cc:398-405); the others return EGG_ERR_UNSUPPORTED. */
+enum egg_integrator { EGG_EXPLICIT_EULER = 0, EGG_OPEN_DYNAMICS_ENGINE = 1, EGG_IMPLICIT_MIDPOINT = 2 };
+
+/* Which solver ComputeVDot uses.  0 is what the reference ships (ensembles.cc:21,531);
+ * 1..3 are sparse_iterations.h:26-34 wired into the same slot. */
+enum egg_solver { EGG_SOLVER_DENSE_MURTY = 0, EGG_SOLVER_PGS = 1, EGG_SOLVER_JACOBI = 2, EGG_SOLVER_SOR = 3 };
+
+/* Constraint-force-mixing policy on the dense path (ensembles.cc:514-521).  AUTO reproduces the
+ * reference's "condition number >= 1e7 => add cfm" decision. */
+enum egg_cfm_mode { EGG_CFM_AUTO = 0, EGG_CFM_ALWAYS = 1, EGG_CFM_NEVER = 2 };
+
+/* Reference quirks kept behind flags (SURVEY.md §8 q1,q2); EGG_QUIRKS_REFERENCE = both on. */
+enum egg_quirk {
+  EGG_QUIRK_GS_BOUNDS_SHIFT = 1,      /* sparse_iterations_utils.cc:169,180,229-235 */
+  EGG_QUIRK_DENSE_IGNORES_BOUNDS = 2  /* lcp.cc:298 -> :141-147 */
+};
+#define EGG_QUIRKS_REFERENCE 3
+
+/* Per-world status bits (egg_get_status). */
+enum egg_status {
+  EGG_ST_OK = 0,
+  EGG_ST_LCP_FAILED = 1,        /* ensembles.cc:531-534 would Panic */
+  EGG_ST_JOINT_CONFLICT = 2,    /* ensembles.cc:280-285 would Panic */
+  EGG_ST_BAD_INIT = 4,          /* ensembles.cc:27 CHECK_MSG would fail */
+  EGG_ST_CONTACT_OVERFLOW = 8,  /* more contacts than max_contacts; the tail was dropped */
+  EGG_ST_NONFINITE = 16         /* NaN/Inf reached the state */
+};
+
+/* Compile-time constants of the reference gathered into one POD (SURVEY.md §5 "Config"):
+ * constants.h:5-12, ensembles.cc:14-21, ensembles.h:165-166, sparse_iterations.cc:15-19. */
+typedef struct egg_desc {
+  int n_worlds;     /* W independent ensembles */
+  int n_bodies;     /* bodies per world (Ensemble::n_, ensembles.h:75) */
+  int n_joints;     /* ball-and-socket joints per world (ensembles.h:81) */
+  int max_contacts; /* per-world contact capacity after de-duplication; 0 = automatic */
+  int precision;    /* 64 (FP64, reference arithmetic); 32 is reserved */
+  int solver;       /* egg_solver */
+  int k_max;        /* kNumIterations = 500 */
+  double tol;       /* kAllowNumericalError = 1e-9 */
+  double cfm;       /* kCfmCoeff = 0.01 */
+  double erp;       /* error_reduction_param = 0.2 */
+  double gravity[3];            /* kGravity = (0,0,-9.8) */
+  double min_constraint_dist;   /* kMinConstraintDistance = 1e-6 */
+  int quirks;       /* egg_quirk bitmask; EGG_QUIRKS_REFERENCE for parity */
+  int cfm_mode;     /* egg_cfm_mode */
+  int device;       /* CUDA device ordinal */
+  int taps;         /* 1 = keep per-pair parity taps (egg_get_pair_hits); costs memory */
+} egg_desc;
+
+/* Fills *d with the reference defaults for the given shape. */
+int egg_desc_default(egg_desc* d, int n_worlds, int n_bodies, int n_joints);
+
+/* Ensemble construction (ensembles.h:25-29 + the Chain/Cairn ctors, ensembles.cc:668-728). */
+int egg_create(const egg_desc* d, egg_batch** out);
+void egg_destroy(egg_batch* b);
+
+/* Body state: Body::{p_,R_,v_,w_,m_,I_,side_lengths_} (body.h:79-91).  side may be NULL
+ * (0.3,0.3,0.3 as body.h:91). */
+int egg_set_bodies(egg_batch* b, const double* p, const double* R, const double* v, const double* w,
+                   const double* m, const double* I_body, const double* side);
+/* Dynamic state only (SetP/SetR/SetV/SetW_GlobalFrame, body.h:64-71). */
+int egg_set_state(egg_batch* b, const double* p, const double* R, const double* v, const double* w);
+/* BallAndSocketJoint(b0,i0,c0,b1,i1,c1) / (b0,i0,c0,c1_world) (joints.h:34-42); i1 = -1 anchors
+ * body i0 to the world point c1. */
+int egg_set_joints(egg_batch* b, const int* i0, const int* i1, const double* c0, const double* c1);
+/* Overrides Ensemble::external_force_torque_ (ensembles.h:88-89) after egg_init; 6 per body. */
+int egg_set_external(egg_batch* b, const double* f_ext);
+
+/* Ensemble::Init (ensembles.cc:24-29): M^-1 blocks, f_ext, initial-condition check. */
+int egg_init(egg_batch* b);
+
+/* n_steps x Ensemble::Step(dt, integrator) (ensembles.cc:390-427) on every world; asynchronous on
+ * the batch stream. */
+int egg_step(egg_batch* b, double dt, int integrator, int n_steps);
+
+/* Reads back Body state (body.h:50-58 accessors); synchronises the stream. */
+int egg_get_bodies(egg_batch* b, double* p, double* R, double* v, double* w);
+
+/* Parity taps of the last step: the surviving contact list in reference order (ensembles.cc:445-480
+ * after :241-329), its multipliers and per-row state.  Any pointer may be NULL.  Layouts:
+ * count[W]; i0,i1,code [W][max_contacts]; pos,nrm [W][max_contacts][3]; depth [W][max_contacts];
+ * lambda [W][3*(n_joints+max_contacts)] in row order (joints first, ensembles.cc:234-239);
+ * row_state same shape: 0 free, 1 at lower bound, 2 at upper bound, 3 equality row. */
+int egg_get_contacts(egg_batch* b, int* count, int* i0, int* i1, double* pos, double* nrm,
+                     double* depth, int* code, double* lambda, int* row_state);
+
+/* Colliding pairs of the last step in (i<j) lexicographic order with CollisionInfo.code and the
+ * pre-de-dup contact count (requires desc.taps = 1).  n_hits[W]; pi,pj,code,count [W][max_pairs]. */
+int egg_get_pair_hits(egg_batch* b, int* n_hits, int* pi, int* pj, int* code, int* count, int max_pairs);
+
+/* status[W] (egg_status bits); stats [W][8] = {n_contacts_raw, n_contacts, n_rows, n_pair_hits,
+ * sweeps, pivots, cfm_applied, reserved}; residual[W] = last GetResidualError. */
+int egg_get_status(egg_batch* b, int* status, int* stats, double* residual);
+
+/* MPC rollout cost per world written to a DEVICE buffer of n_worlds doubles (feeds the NCCL
+ * allgather): cost = -(x_body0 - x0_body0) + 10 (z_body0 - z0_body0)^2 with (x0,z0) the pose at
+ * egg_init.  The reference has no cost function; this definition is ours. */
+int egg_rollout_costs(egg_batch* b, double* cost_d);
+
+/* Stream plumbing: run the batch on a caller-owned cudaStream_t (e.g. torch's current stream) so
+ * that caller-side CUDA events bracket the kernels. */
+int egg_set_stream(egg_batch* b, void* cuda_stream);
+int egg_sync(egg_batch* b);
+
+/* Per-world contact capacity actually allocated (max_contacts after rounding / the automatic rule). */
+int egg_capacity(const egg_batch* b);
+
+/* Bytes of device memory held by the batch; number of kernel launches issued so far. */
+long long egg_device_bytes(const egg_batch* b);
+long long egg_launch_count(const egg_batch* b);
+
+/* Pinned host staging (cudaHostAlloc) for end-to-end measurements. */
+void* egg_host_alloc(long long bytes);
+void egg_host_free(void* p);
+
+const char* egg_last_error(void);
+const char* egg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGG_CUDA_H_ */
