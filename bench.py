@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — world-steps/sec of the batched rigid-body step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3]
+
+One "step" = one Ensemble::Step (narrowphase -> rows -> PGS -> integrate) over every world of the
+rank's batch.  Default workload = BASELINE.json configs[2], the configuration the metric's target
+is quoted on ("64-body contact-rich stacks"): W worlds x 64-body pile per GPU, PGS with the
+reference's termination (<= 500 sweeps, residual <= 1e-9, cfm 0.01), dt = 0.005, FP64.
+Weak scaling: every rank owns the same number of worlds; the only collective is one NCCL
+allgather of the per-world rollout costs at the end of the timed horizon.
+
+Prints ONE JSON line on rank 0 (see the driver contract in the task statement).
+`--impl reference` times the CPU restatement of the reference step (oracle/, kind "port": the
+reference itself cannot be built here — Eigen/Qt/glog are absent) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene fn name, kwargs, default worlds per GPU, description)
+    "c2": ("stack10", {}, 4096, "4096 worlds x 10-box stack on ground plane, contact-only PGS"),
+    "c3": ("pile64", {}, 65536, "65536 worlds x 64-body random box pile, contact-rich PGS"),
+    "c5": ("legged20", {}, 131072, "worlds x 20-body legged ensemble (19 ball joints + foot contacts), PGS"),
+}
+FLOPS_PER_ROW_UPDATE = 54.0
+ROW_STREAM_BYTES = 240.0      # one row streamed from HBM
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--worlds", type=int, default=0, help="worlds per GPU (0 = the workload's default)")
+    ap.add_argument("--k-max", type=int, default=500)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def scene_for(args, W, rank):
+    import eggshell_b200 as E
+    fn, kw, _, _ = WORKLOADS[args.workload]
+    base = {"stack10": 1000, "pile64": 3000, "legged20": 5000}[fn]
+    return getattr(E.scenes, fn)(W, seed=[base, rank], **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port) — the only place bench.py executes oracle/.
+def cpu_reference(args, cores, seconds, steps_per_sample=1):
+    """Times the CPU port of Ensemble::Step on `cores` threads over a bounded sample of the same
+    workload.  Returns dict(value, unit, cores, kind, sample, rows_per_s)."""
+    from oracle import pyoracle as O
+    from tests.helpers import oracle_world
+    fn, kw, _, _ = WORKLOADS[args.workload]
+    # calibrate with one world-step on one thread
+    sc = scene_for(args, 1, 0)
+    w0, _ = oracle_world(sc, 0, solver=1, k_max=args.k_max)
+    t0 = time.perf_counter()
+    w0.step(sc["dt"])
+    t1 = time.perf_counter() - t0
+    per_core = max(1, int(seconds / max(t1, 1e-6) / max(steps_per_sample, 1)))
+    per_core = min(per_core, 4096)
+    nw = per_core * cores
+    sc = scene_for(args, nw, 0)
+    worlds = [oracle_world(sc, w, solver=1, k_max=args.k_max)[0] for w in range(nw)]
+    sec, rows_sweeps, rows = O.batch_step(worlds, sc["dt"], steps_per_sample, cores)
+    ws = nw * steps_per_sample
+    return dict(value=ws / sec, unit="world-steps/s", cores=cores, kind="port",
+                sample=f"{nw} worlds x {steps_per_sample} step(s) of {WORKLOADS[args.workload][3]} on {cores} host threads "
+                       f"({sec:.2f} s); oracle/ = Eigen-free restatement of the reference step, g++ -O2 -march=native",
+                rows_per_s=rows_sweeps / sec, seconds=sec, world_steps=ws)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as O
+    cores = O.hardware_concurrency() or os.cpu_count() or 1
+    total = args.steps + args.warmup
+    per_step = max(2.0, min(20.0, 120.0 / max(total, 1)))
+    # warm-up samples (untimed), then K timed samples
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference(args, cores, 1.0)
+    vals, sec, ws, rps = [], 0.0, 0, 0.0
+    res = None
+    for _ in range(args.steps):
+        res = cpu_reference(args, cores, per_step)
+        sec += res["seconds"]
+        ws += res["world_steps"]
+        rps += res["rows_per_s"] * res["seconds"]
+    value = ws / sec
+    fn, kw, Wd, desc = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": "world-steps/sec", "value": value, "unit": "world-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "solver": "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01,
+                   "dt": 0.005, "inputs": "bounded CPU sample of the same workload per step"},
+        "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": res["sample"]},
+        "pgs_rows_per_s": rps / sec,
+        "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import eggshell_b200 as E
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: eggshell_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    fn, kw, Wd, desc = WORKLOADS[args.workload]
+    W = args.worlds or Wd
+    scene = scene_for(args, W, rank)
+    n, nj, dt = scene["n"], scene["nj"], scene["dt"]
+    maxc = {"c3": 1024, "c2": 0, "c5": 0}[args.workload]
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=args.k_max, max_contacts=maxc, device=local)
+    stream = torch.cuda.current_stream()
+    b.set_stream(stream.cuda_stream)
+    costs = torch.zeros(W, dtype=torch.float64, device="cuda")
+    all_costs = torch.zeros(W * world, dtype=torch.float64, device="cuda") if world > 1 else costs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # Every step starts from the named scene's state (device-resident snapshot), so all K steps
+    # do the same work: step = egg_restore (D2D, inside the timed region) + egg_step.
+    b.snapshot()
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 0)):
+        b.restore()
+        b.step(dt)
+    b.sync()
+    b.set_profiling(True)
+    b.kernel_ms()
+    launches0 = b.launch_count
+
+    # ---- timed region: K steps + cost kernel + the one collective ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        b.restore()
+        b.step(dt)
+    b.rollout_costs(costs.data_ptr())
+    if world > 1:
+        dist.all_gather_into_tensor(all_costs, costs)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = b.launch_count - launches0
+    kms = b.kernel_ms()
+    b.set_profiling(False)
+    st = b.status()
+    rows_last = float(st["n_rows"].astype(np.float64).sum())
+    sweeps_last = float((st["n_rows"].astype(np.float64) * st["sweeps"]).sum())
+    contacts_mean = float(st["n_contacts"].mean())
+    status_or = int(np.bitwise_or.reduce(st["status"]))
+    best = float(all_costs.min().item())
+
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = W * world * args.steps / (ms_max * 1e-3)
+
+    # ---- end-to-end: host state in pinned memory -> H2D -> step -> D2H, every step ----
+    # inputs = the scene's initial state in pinned host memory; outputs land in a second pinned set
+    hin = (E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3, 3)), E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3)))
+    hout = (E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3, 3)), E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3)))
+    for dst, src in zip(hin, (scene["p"], scene["R"], scene["v"], scene["w"])):
+        dst[...] = src
+    h2d = d2h = sum(x.nbytes for x in hin)
+    for _ in range(1):
+        b.set_state(*hin); b.step(dt); b.bodies(out=hout)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.e2e_steps):
+        b.set_state(*hin)                # egg_set_state: pinned host -> device (+ SoA pack kernels)
+        b.step(dt)                       # egg_step
+        b.bodies(out=hout)               # egg_get_bodies: device -> pinned host (syncs)
+    f1.record(stream)
+    barrier()
+    t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = W * world * args.e2e_steps / (float(t2.item()) * 1e-3)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        steps_counted = max(kms[3], 1.0)
+        solve_ms = kms[2] / steps_counted
+        bytes_step = E.scenes.algorithmic_bytes_per_world_step(n, nj)
+        nc_mean = rows_last / W / 3.0
+        # dominant kernel = solve + integrate: state in/out + static + every row streamed once
+        solve_bytes = W * (bytes_step + 3.0 * nc_mean * ROW_STREAM_BYTES)
+        achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "egg_pgs_kernel (PGS solve + fused integrate)", "achieved": achieved,
+                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_source": pk_kind,
+                "traffic": None, "kernel_ms": solve_ms, "kernel_share_of_step": kms[2] / max(kms[0] + kms[1] + kms[2], 1e-9),
+                "algorithmic_bytes_per_launch": solve_bytes}
+        try:
+            fp64_peak = E.batch.fp64_peak_tflops(local)
+        except Exception:
+            fp64_peak = None
+        flops = FLOPS_PER_ROW_UPDATE * sweeps_last
+        roof64 = {"bound": "fp64", "achieved": flops / (solve_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                  "frac": (flops / (solve_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+                  "peak_source": "DFMA microbenchmark (egg_fp64_peak_tflops), this run",
+                  "flops_per_row_update": FLOPS_PER_ROW_UPDATE}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import pyoracle as O
+            cpu = cpu_reference(args, O.hardware_concurrency() or 1, args.cpu_seconds)
+            cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "rows_per_s")}
+        line = {
+            "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "worlds_per_gpu": W, "bodies": n, "joints": nj,
+                       "solver": "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01, "dt": dt, "parallelism": f"worlds sharded x{world}",
+                       "step": "every timed step = egg_restore(scene state, D2D) + egg_step: all steps do the same work",
+                       "l2": "inputs larger than L2 (state %.0f MB + rows %.0f MB per rank)" % (W * n * 34 * 8 / 1e6, W * nc_mean * 256 / 1e6),
+                       "mean_contacts_per_world": contacts_mean, "mean_rows_per_world": rows_last / W,
+                       "mean_sweeps": sweeps_last / max(rows_last, 1.0), "status_or": status_or, "best_cost": best},
+            "pgs_rows_per_s": sweeps_last / (solve_ms * 1e-3),
+            "kernel_ms_per_step": {"narrowphase": kms[0] / steps_counted, "assembly": kms[1] / steps_counted, "solve_integrate": solve_ms},
+            "roofline": roof, "roofline_fp64": roof64, "cpu_baseline": cpu, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": args.e2e_steps, "api": "egg_set_state + egg_step + egg_get_bodies (pinned host buffers)"},
+            "gpu_launches": int(launches),
+        }
+        print(json.dumps(line), flush=True)
+    b.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

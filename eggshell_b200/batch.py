@@ -22,9 +22,9 @@ ST_LCP_FAILED, ST_JOINT_CONFLICT, ST_BAD_INIT, ST_CONTACT_OVERFLOW, ST_NONFINITE
 
 EXPORTS = [
     "egg_desc_default", "egg_create", "egg_destroy", "egg_set_bodies", "egg_set_state", "egg_set_joints",
-    "egg_set_external", "egg_init", "egg_step", "egg_get_bodies", "egg_get_contacts", "egg_get_pair_hits",
+    "egg_set_external", "egg_init", "egg_step", "egg_snapshot", "egg_restore", "egg_get_bodies", "egg_get_contacts", "egg_get_pair_hits",
     "egg_get_status", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
-    "egg_launch_count", "egg_capacity", "egg_host_alloc", "egg_host_free", "egg_last_error", "egg_version",
+    "egg_launch_count", "egg_capacity", "egg_set_profiling", "egg_get_kernel_ms", "egg_fp64_peak_tflops", "egg_host_alloc", "egg_host_free", "egg_last_error", "egg_version",
 ]
 
 
@@ -59,6 +59,7 @@ def lib():
         L.egg_device_bytes.restype = C.c_longlong
         L.egg_launch_count.restype = C.c_longlong
         L.egg_host_alloc.restype = C.c_void_p
+        L.egg_fp64_peak_tflops.restype = C.c_double
         L.egg_host_alloc.argtypes = [C.c_longlong]
         L.egg_host_free.argtypes = [C.c_void_p]
         L.egg_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -164,6 +165,12 @@ class Batch:
     def step(self, dt, n_steps=1, integrator=OPEN_DYNAMICS_ENGINE):
         _chk(lib().egg_step(self.h, C.c_double(dt), int(integrator), int(n_steps)), "egg_step")
 
+    def snapshot(self):
+        _chk(lib().egg_snapshot(self.h), "egg_snapshot")
+
+    def restore(self):
+        _chk(lib().egg_restore(self.h), "egg_restore")
+
     def sync(self):
         _chk(lib().egg_sync(self.h), "egg_sync")
 
@@ -207,6 +214,15 @@ class Batch:
     def rollout_costs(self, device_ptr):
         _chk(lib().egg_rollout_costs(self.h, C.c_void_p(device_ptr)), "egg_rollout_costs")
 
+    def set_profiling(self, on=True):
+        _chk(lib().egg_set_profiling(self.h, int(on)), "egg_set_profiling")
+
+    def kernel_ms(self):
+        """(narrowphase, assembly, solve+integrate) device milliseconds and the steps they cover."""
+        out = np.zeros(4)
+        _chk(lib().egg_get_kernel_ms(self.h, _p(out)), "egg_get_kernel_ms")
+        return out
+
     @property
     def device_bytes(self):
         return lib().egg_device_bytes(self.h)
@@ -214,3 +230,10 @@ class Batch:
     @property
     def launch_count(self):
         return lib().egg_launch_count(self.h)
+
+
+def fp64_peak_tflops(device=0):
+    v = lib().egg_fp64_peak_tflops(int(device))
+    if v < 0:
+        raise EggError(f"egg_fp64_peak_tflops failed ({v}): {lib().egg_last_error().decode()}")
+    return v

@@ -15,6 +15,7 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relax
 UNITS = [
     ("egg_collide.cu", ["-fmad=false"]),
     ("egg_solve.cu", []),
+    ("egg_pgs.cu", []),
     ("egg_dense.cu", ["-fmad=false"]),
     ("egg_capi.cu", []),
 ]

@@ -12,6 +12,7 @@
 
 void egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes);
 size_t egg_dense_scratch_bytes(const EggDev& d);
+double egg_measure_fp64_tflops();
 
 static thread_local std::string g_err;
 static void set_err(const char* what, cudaError_t e) {
@@ -42,6 +43,10 @@ struct egg_batch {
   void* dense_scratch = nullptr;
   size_t dense_scratch_bytes = 0;
   int device = 0;
+  double* snap = nullptr;        // egg_snapshot copy of dev.dyn
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev;   // 4 per profiled step
+  std::vector<cudaEvent_t> ev_free;
 };
 
 template <class T>
@@ -174,6 +179,8 @@ void egg_destroy(egg_batch* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (void* p : b->allocs) cudaFree(p);
+  for (cudaEvent_t e : b->ev) cudaEventDestroy(e);
+  for (cudaEvent_t e : b->ev_free) cudaEventDestroy(e);
   if (b->own_stream && b->stream) cudaStreamDestroy(b->stream);
   delete b;
 }
@@ -196,6 +203,34 @@ int egg_sync(egg_batch* b) {
   return EGG_OK;
 }
 
+int egg_set_profiling(egg_batch* b, int on) {
+  if (!b) return EGG_ERR_ARG;
+  b->profiling = on != 0;
+  return EGG_OK;
+}
+int egg_get_kernel_ms(egg_batch* b, double* out4) {
+  if (!b || !out4) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  CK(cudaStreamSynchronize(b->stream));
+  for (int k = 0; k < 4; k++) out4[k] = 0;
+  for (size_t s = 0; s + 3 < b->ev.size(); s += 4) {
+    for (int k = 0; k < 3; k++) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, b->ev[s + k], b->ev[s + k + 1]));
+      out4[k] += ms;
+    }
+    out4[3] += 1;
+  }
+  for (cudaEvent_t e : b->ev) b->ev_free.push_back(e);
+  b->ev.clear();
+  return EGG_OK;
+}
+double egg_fp64_peak_tflops(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err = "no CUDA device"; return (double)EGG_ERR_NO_DEVICE; }
+  if (cudaSetDevice(device) != cudaSuccess) return (double)EGG_ERR_ARG;
+  return egg_measure_fp64_tflops();
+}
 int egg_capacity(const egg_batch* b) { return b ? b->dev.maxc : 0; }
 long long egg_device_bytes(const egg_batch* b) { return b ? b->bytes : 0; }
 long long egg_launch_count(const egg_batch* b) { return b ? b->launches : 0; }
@@ -308,13 +343,45 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
   }
   CK(cudaSetDevice(b->device));
   for (int s = 0; s < n_steps; s++) {
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (b->profiling) {
+      for (int k = 0; k < 4; k++) {
+        if (!b->ev_free.empty()) { e[k] = b->ev_free.back(); b->ev_free.pop_back(); }
+        else CK(cudaEventCreate(&e[k]));
+        b->ev.push_back(e[k]);
+      }
+      CK(cudaEventRecord(e[0], b->stream));
+    }
     egg_launch_collide(b->dev, b->stream);
+    if (b->profiling) CK(cudaEventRecord(e[1], b->stream));
     egg_launch_assemble(b->dev, dt, b->stream);
+    if (b->profiling) CK(cudaEventRecord(e[2], b->stream));
     if (solver == EGG_SOLVER_PGS) egg_launch_solve_pgs(b->dev, dt, b->stream);
     else egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes);
+    if (b->profiling) CK(cudaEventRecord(e[3], b->stream));
     b->launches += 3;
   }
   CK(cudaGetLastError());
+  return EGG_OK;
+}
+
+int egg_snapshot(egg_batch* b) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const size_t cnt = (size_t)b->dev.W * EGG_DYN * b->dev.n;
+  if (!b->snap) {
+    int r = dalloc(b, &b->snap, cnt);
+    if (r != EGG_OK) return r;
+  }
+  CK(cudaMemcpyAsync(b->snap, b->dev.dyn, cnt * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
+  return EGG_OK;
+}
+int egg_restore(egg_batch* b) {
+  if (!b) return EGG_ERR_ARG;
+  if (!b->snap) { g_err = "egg_restore before egg_snapshot"; return EGG_ERR_STATE; }
+  CK(cudaSetDevice(b->device));
+  const size_t cnt = (size_t)b->dev.W * EGG_DYN * b->dev.n;
+  CK(cudaMemcpyAsync(b->dev.dyn, b->snap, cnt * sizeof(double), cudaMemcpyDeviceToDevice, b->stream));
   return EGG_OK;
 }
 

@@ -6,7 +6,10 @@
 //   bpar   [W][13][n]   side(3) m I_b(9)                        body.h:81,85,91
 //   joints [W][nj] i0,i1 ; jc [W][6][nj] c0(3) c1(3)            joints.h:26-28
 //   contacts: c_i0,c_i1,c_code [W][maxc]; c_geom [W][7][maxc] pos(3) nrm(3) depth
-//   records [W][nrec][32 doubles] in dependency-level order, lam [W][nrec][3]
+//   records [W][nrec] x 240 B in dependency-level order; inside one level chunk (<= 32 blocks,
+//           one solver stage) the 15 16-byte pieces are stored piece-major: [piece][block], so a
+//           stage is one contiguous TMA bulk copy and lanes read consecutive 16-byte words;
+//           lam [W][nrec][3]
 // The body index is the fastest-varying one inside a world so that a warp working on one world
 // reads/writes contiguous 8-byte lanes; a world is one contiguous chunk (TMA-bulk friendly).
 #pragma once
@@ -17,7 +20,8 @@
 #define EGG_DYN 18
 #define EGG_STAT 16
 #define EGG_BPAR 13
-#define EGG_REC 32          // doubles per constraint record
+#define EGG_REC 30          // doubles per constraint record (15 x 16-byte pieces = 240 B)
+#define EGG_PIECES 15
 #define EGG_MAX_POLY 12
 #define EGG_MAX_PAIR_CONTACTS 10
 
@@ -31,7 +35,6 @@
 #define REC_RHS 24          // 3
 #define REC_IDX 27          // int2: i0, i1
 #define REC_META 28         // int2: original constraint index, clamp kind
-#define REC_ERR 29          // 3: position error rows (diagnostic)
 
 // Clamp kinds of a 3-row block.
 #define KIND_EQUALITY 0     // joints: no projection
@@ -62,8 +65,8 @@ struct EggDev {
   double* lam;                // [W][nrec][3] level order during the solve
   double* lam_out;            // [W][3*nrec] row order (joints then contacts)
   int* row_state;             // [W][3*nrec]
-  int* level_start;           // [W][nrec+1]
-  int* n_levels;              // [W]
+  int* level_start;           // [W][nrec+1] start slot of every solver stage (level chunk <= 32 blocks)
+  int* n_levels;              // [W] number of stages
   int* status;                // [W]
   int* stats;                 // [W][8]
   double* resid;              // [W]

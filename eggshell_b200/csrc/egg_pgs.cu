@@ -1,0 +1,972 @@
+// Constraint-row assembly and the projected Gauss-Seidel solve with fused integrate.
+//
+// Replaces (per world):
+//   egg_assemble_kernel  Joint/Contact::ComputeJ + error  joints.cc:3-35, contact.cc:14-117,
+//                        Ensemble::ComputeJ / rhs         ensembles.cc:38-87, 156-171, 563-570
+//   egg_pgs_kernel       sparse::GaussSeidelIteration     sparse_iterations.cc:148-226, 51-69,
+//                        matrix-free block ops            sparse_iterations_utils.cc:12-21,159-243,495-695
+//                        + v' = v + dt M^-1 (f + J^T x)   ensembles.cc:535, 572-573
+//                        + StepPositions_ODE / WtoQ       ensembles.cc:577-591, utils.cc:82-89
+//
+// Formulation.  Every constraint (joint or contact) is one 3-row block whose two 3x6 Jacobians
+// are [-Rc, Rc [r0]x] and [Rc, -Rc [r1]x] (contact.cc:60-75; a ball joint is the same shape with
+// Rc = -I, joints.cc:22-30).  Instead of streaming 2x3x6 Jacobian entries per block the kernels
+// keep a compact 240-byte record (Rc, r0, r1, the 3x3 diagonal block D of J M^-1 J^T, rhs) and
+// the body-space accumulator a = M^-1 J^T x (6 doubles per body, in shared memory).  One block
+// update is  t = Rc (vel1(a) - vel0(a)),  row-by-row projected substitution inside the 3x3
+// diagonal block exactly as sparse_iterations_utils.cc:229-236, and an impulse scatter into a.
+//
+// Schedule.  Gauss-Seidel is sequential in constraint order, but blocks that share no body
+// commute exactly.  Blocks are grouped into dependency levels (level(c) = 1 + max level of any
+// earlier block sharing a body) and levels are cut into stages of <= 32 blocks; running stage
+// after stage with one lane per block is bit-identical to the sequential sweep.
+//
+// Execution.  One warp (one CTA) owns one world for all of its sweeps.  A stage's records are one
+// contiguous piece-major chunk in HBM/L2; lane 0 streams it into a shared-memory ring with a
+// single TMA bulk copy (cp.async.bulk + mbarrier complete_tx) NSTAGE-1 stages ahead of its use,
+// so the dependent FP64 chain of a stage never waits on L2.  Stages are separated by
+// __syncwarp() only.
+#include "egg_internal.cuh"
+
+namespace {
+
+// Eigen 3.3 Quaternion::FromTwoVectors(normal, z).toRotationMatrix()  (utils.cc:233-236).  The
+// exactly anti-parallel case uses the same pinned rule as the oracle (orc_linalg.h).
+__device__ inline void align_to_z(d3 nrm, double* R) {
+  double z2 = dot3(nrm, nrm);
+  d3 v0 = (z2 > 0) ? nrm / sqrt(z2) : nrm;
+  double c = v0.z;   // dot(v1 = (0,0,1), v0)
+  double qw, qx, qy, qz;
+  if (c < -1.0 + 1e-12) {
+    c = fmax(c, -1.0);
+    int k = 0;
+    if (fabs(v0.y) < fabs(get3(v0, k))) k = 1;
+    if (fabs(v0.z) < fabs(get3(v0, k))) k = 2;
+    d3 e = mk3(k == 0, k == 1, k == 2);
+    d3 ax = cross3(v0, e);
+    double a2 = dot3(ax, ax);
+    if (a2 > 0) ax = ax / sqrt(a2);
+    double w2 = (1.0 + c) * 0.5;
+    qw = sqrt(w2);
+    double s = sqrt(1.0 - w2);
+    qx = ax.x * s; qy = ax.y * s; qz = ax.z * s;
+  } else {
+    d3 ax = cross3(v0, mk3(0, 0, 1));
+    double s = sqrt((1.0 + c) * 2.0);
+    double invs = 1.0 / s;
+    qx = ax.x * invs; qy = ax.y * invs; qz = ax.z * invs;
+    qw = s * 0.5;
+  }
+  double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Assembly: one CTA per world.  Thread 0 computes the dependency levels / stages from the body
+// indices staged in shared memory; then one thread per constraint builds its record and writes
+// it at its (stage, lane) position in piece-major order.
+template <int NT>
+__global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, int stage_cap) {
+  extern __shared__ double sm[];
+  const int n = d.n, nj = d.nj, w = blockIdx.x, tid = threadIdx.x;
+  double* sdyn = sm;                         // [18][n]
+  double* sst = sm + EGG_DYN * n;            // [16][n]
+  int* si0 = (int*)(sm + (EGG_DYN + EGG_STAT) * n);   // [nrec]
+  int* si1 = si0 + d.nrec;                   // [nrec]
+  int* slot = si1 + d.nrec;                  // [nrec] record slot of c
+  int* lev = slot + d.nrec;                  // [nrec] dependency level of c
+  int* lstart = lev + d.nrec;                // [nrec + 1] level counts -> running slot cursor
+  int* lstage = lstart + d.nrec + 1;         // [nrec + 1] first stage of each level
+  int* lfirst = lstage + d.nrec + 1;         // [nrec + 1] first slot of each level
+  int* blast = lfirst + d.nrec + 1;          // [n] last level that touched the body
+  const double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+  const double* st = d.stat + (size_t)w * EGG_STAT * n;
+  for (int i = tid; i < EGG_DYN * n; i += NT) sdyn[i] = dyn[i];
+  for (int i = tid; i < EGG_STAT * n; i += NT) sst[i] = st[i];
+  const int ncon = d.c_count[w];
+  const int nc = nj + ncon;
+  const int* c_i0 = d.c_i0 + (size_t)w * d.maxc;
+  const int* c_i1 = d.c_i1 + (size_t)w * d.maxc;
+  const double* geom = d.c_geom + (size_t)w * 7 * d.maxc;
+  const int maxc = d.maxc;
+  for (int c = tid; c < nc; c += NT) {
+    if (c < nj) { si0[c] = d.j_i0[(size_t)w * nj + c]; si1[c] = d.j_i1[(size_t)w * nj + c]; }
+    else { si0[c] = c_i0[c - nj]; si1[c] = c_i1[c - nj]; }
+  }
+  for (int b = tid; b < n; b += NT) blast[b] = -1;
+  for (int c = tid; c <= nc; c += NT) lstart[c] = 0;
+  __syncthreads();
+
+  int* gstage = d.level_start + (size_t)w * (d.nrec + 1);
+  if (tid == 0) {
+    int nl = 0;
+    for (int c = 0; c < nc; c++) {           // reference order: joints, then contacts
+      const int i0 = si0[c], i1 = si1[c];
+      int l = -1;
+      if (i0 >= 0) l = max(l, blast[i0]);
+      if (i1 >= 0) l = max(l, blast[i1]);
+      l += 1;
+      if (i0 >= 0) blast[i0] = l;
+      if (i1 >= 0) blast[i1] = l;
+      lev[c] = l;
+      lstart[l]++;
+      nl = max(nl, l + 1);
+    }
+    int ns = 0, run = 0;
+    for (int l = 0; l < nl; l++) {
+      const int cnt = lstart[l];
+      lfirst[l] = run;
+      lstart[l] = run;                       // running cursor of the level
+      lstage[l] = ns;
+      for (int k = 0; k < cnt; k += stage_cap) gstage[ns++] = run + k;
+      run += cnt;
+    }
+    gstage[ns] = nc;
+    d.n_levels[w] = ns;
+    for (int c = 0; c < nc; c++) slot[c] = lstart[lev[c]]++;   // stable inside a level
+  }
+  __syncthreads();
+
+  const double erp = d.prm.erp, cfm = d.prm.cfm;
+  const bool shift = (d.prm.quirks & 1) != 0;
+  double* recw = d.rec + (size_t)w * d.nrec * EGG_REC;
+  for (int c = tid; c < nc; c += NT) {
+    const int i0 = si0[c], i1 = si1[c];
+    int kind;
+    double Rc[9];
+    d3 r0 = mk3(0, 0, 0), r1 = mk3(0, 0, 0), err;
+    if (c < nj) {
+      const double* jc = d.jc + (size_t)w * 6 * nj;
+      d3 c0 = mk3(jc[c], jc[nj + c], jc[2 * nj + c]);
+      d3 c1 = mk3(jc[3 * nj + c], jc[4 * nj + c], jc[5 * nj + c]);
+      for (int k = 0; k < 9; k++) Rc[k] = 0;
+      Rc[0] = Rc[4] = Rc[8] = -1.0;
+      double R0[9];
+      for (int k = 0; k < 9; k++) R0[k] = sdyn[(3 + k) * n + i0];
+      r0 = mmulv(R0, c0);
+      d3 p0 = mk3(sdyn[i0], sdyn[n + i0], sdyn[2 * n + i0]);
+      if (i1 < 0) {
+        err = p0 + r0 - c1;                       // joints.cc:6
+      } else {
+        double R1[9];
+        for (int k = 0; k < 9; k++) R1[k] = sdyn[(3 + k) * n + i1];
+        r1 = mmulv(R1, c1);
+        d3 p1 = mk3(sdyn[i1], sdyn[n + i1], sdyn[2 * n + i1]);
+        err = p0 + r0 - p1 - r1;                  // joints.cc:8
+      }
+      kind = KIND_EQUALITY;
+    } else {
+      const int k = c - nj;
+      d3 pos = mk3(geom[0 * maxc + k], geom[1 * maxc + k], geom[2 * maxc + k]);
+      d3 nrm = mk3(geom[3 * maxc + k], geom[4 * maxc + k], geom[5 * maxc + k]);
+      align_to_z(nrm, Rc);
+      if (i0 >= 0) r0 = pos - mk3(sdyn[i0], sdyn[n + i0], sdyn[2 * n + i0]);
+      if (i1 >= 0) r1 = pos - mk3(sdyn[i1], sdyn[n + i1], sdyn[2 * n + i1]);
+      err = mk3(0, 0, -geom[6 * maxc + k]);      // contact.cc:14-22
+      kind = KIND_CONTACT;
+    }
+    // q2: the matrix-free lower-triangular solve projects block c > 0 with the (type, lo, hi) of
+    // block c-1 (sparse_iterations_utils.cc:169,180,229-235).
+    int ckind = kind;
+    if (shift && c > 0) ckind = (c - 1 < nj) ? KIND_EQUALITY : KIND_CONTACT;
+
+    // Jacobian rows: body0 lin = -Rc_k, ang = Rc_k x r0 ; body1 lin = Rc_k, ang = r1 x Rc_k.
+    d3 jl[3], ja0[3], ja1[3];
+    for (int k = 0; k < 3; k++) {
+      jl[k] = mrow(Rc, k);
+      ja0[k] = cross3(jl[k], r0);
+      ja1[k] = cross3(r1, jl[k]);
+    }
+    // D = J0 M0^-1 J0^T + J1 M1^-1 J1^T and J u with u = v/dt + M^-1 f (ensembles.cc:569-570).
+    double D[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double Ju[3] = {0, 0, 0};
+    for (int side = 0; side < 2; side++) {
+      const int b = side ? i1 : i0;
+      if (b < 0) continue;
+      const double mi = sst[b];
+      double Ii[9];
+      for (int k = 0; k < 9; k++) Ii[k] = sst[(1 + k) * n + b];
+      const double sg = side ? 1.0 : -1.0;
+      d3 v = mk3(sdyn[12 * n + b], sdyn[13 * n + b], sdyn[14 * n + b]);
+      d3 wv = mk3(sdyn[15 * n + b], sdyn[16 * n + b], sdyn[17 * n + b]);
+      d3 fl = mk3(sst[10 * n + b], sst[11 * n + b], sst[12 * n + b]);
+      d3 ft = mk3(sst[13 * n + b], sst[14 * n + b], sst[15 * n + b]);
+      d3 ul = v / dt + fl * mi;
+      d3 ua = wv / dt + mmulv(Ii, ft);
+      for (int k = 0; k < 3; k++) {
+        d3 lin = jl[k] * sg;
+        d3 ang = side ? ja1[k] : ja0[k];
+        d3 Ia = mmulv(Ii, ang);
+        for (int l = 0; l < 3; l++) {
+          d3 lin2 = jl[l] * sg;
+          d3 ang2 = side ? ja1[l] : ja0[l];
+          D[3 * k + l] += mi * dot3(lin, lin2) + dot3(Ia, ang2);
+        }
+        Ju[k] += dot3(lin, ul) + dot3(ang, ua);
+      }
+    }
+    double v[EGG_REC];
+    for (int k = 0; k < 9; k++) v[REC_RC + k] = Rc[k];
+    v[REC_R0] = r0.x; v[REC_R0 + 1] = r0.y; v[REC_R0 + 2] = r0.z;
+    v[REC_R1] = r1.x; v[REC_R1 + 1] = r1.y; v[REC_R1 + 2] = r1.z;
+    v[REC_DOFF] = D[3]; v[REC_DOFF + 1] = D[6]; v[REC_DOFF + 2] = D[7];
+    for (int k = 0; k < 3; k++) {
+      v[REC_DDIAG + k] = D[4 * k];
+      v[REC_INVA + k] = 1.0 / (D[4 * k] + cfm);
+      v[REC_RHS + k] = -erp / dt / dt * get3(err, k) - Ju[k];
+    }
+    v[REC_IDX] = __hiloint2double(i1, i0);
+    v[REC_META] = __hiloint2double(ckind, c);
+    v[29] = 0.0;
+    double2* out = reinterpret_cast<double2*>(recw + (size_t)slot[c] * EGG_REC);
+#pragma unroll
+    for (int p = 0; p < EGG_PIECES; p++) out[p] = make_double2(v[2 * p], v[2 * p + 1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared block math (both solver variants).
+
+struct BlockRec {
+  double Rc[9];
+  d3 r0, r1;
+  double doff[3], ddiag[3], inva[3], rhs[3];
+  int i0, i1, orig, kind;
+};
+
+__device__ __forceinline__ void unpack_rec(const double2* v, BlockRec& r) {
+  // pieces: [0..4] Rc0..8 r0.x | [5..7] r0.y r0.z r1 | ... straight double order, see REC_*
+  double f[EGG_REC];
+#pragma unroll
+  for (int p = 0; p < EGG_PIECES; p++) { f[2 * p] = v[p].x; f[2 * p + 1] = v[p].y; }
+#pragma unroll
+  for (int k = 0; k < 9; k++) r.Rc[k] = f[REC_RC + k];
+  r.r0 = mk3(f[REC_R0], f[REC_R0 + 1], f[REC_R0 + 2]);
+  r.r1 = mk3(f[REC_R1], f[REC_R1 + 1], f[REC_R1 + 2]);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    r.doff[k] = f[REC_DOFF + k]; r.ddiag[k] = f[REC_DDIAG + k]; r.inva[k] = f[REC_INVA + k]; r.rhs[k] = f[REC_RHS + k];
+  }
+  r.i0 = __double2loint(f[REC_IDX]); r.i1 = __double2hiint(f[REC_IDX]);
+  r.orig = __double2loint(f[REC_META]); r.kind = __double2hiint(f[REC_META]);
+}
+
+// t = J a for the block: Rc (vel1 - vel0), vel_b = a_lin + a_ang x r_b.
+__device__ __forceinline__ d3 block_Ja(const BlockRec& r, const double* sa, int n) {
+  d3 u = mk3(0, 0, 0);
+  if (r.i1 >= 0) {
+    const int b = r.i1;
+    d3 al = mk3(sa[b], sa[n + b], sa[2 * n + b]);
+    d3 aa = mk3(sa[3 * n + b], sa[4 * n + b], sa[5 * n + b]);
+    u = al + cross3(aa, r.r1);
+  }
+  if (r.i0 >= 0) {
+    const int b = r.i0;
+    d3 al = mk3(sa[b], sa[n + b], sa[2 * n + b]);
+    d3 aa = mk3(sa[3 * n + b], sa[4 * n + b], sa[5 * n + b]);
+    u = u - (al + cross3(aa, r.r0));
+  }
+  return mmulv(r.Rc, u);
+}
+
+// a += M^-1 J^T delta for the block.  minv: [10][n] = 1/m, Iinv (shared or read-only global).
+template <bool LDG>
+__device__ __forceinline__ void block_scatter(const BlockRec& r, d3 delta, double* sa, const double* minv, int n) {
+  d3 imp = mtmulv(r.Rc, delta);
+  if (r.i1 >= 0) {
+    const int b = r.i1;
+    double Ii[9];
+    const double mi = LDG ? __ldg(minv + b) : minv[b];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ii[k] = LDG ? __ldg(minv + (1 + k) * n + b) : minv[(1 + k) * n + b];
+    d3 da = mmulv(Ii, cross3(r.r1, imp));
+    sa[b] += mi * imp.x; sa[n + b] += mi * imp.y; sa[2 * n + b] += mi * imp.z;
+    sa[3 * n + b] += da.x; sa[4 * n + b] += da.y; sa[5 * n + b] += da.z;
+  }
+  if (r.i0 >= 0) {
+    const int b = r.i0;
+    double Ii[9];
+    const double mi = LDG ? __ldg(minv + b) : minv[b];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Ii[k] = LDG ? __ldg(minv + (1 + k) * n + b) : minv[(1 + k) * n + b];
+    d3 da = mmulv(Ii, cross3(r.r0, imp));
+    sa[b] -= mi * imp.x; sa[n + b] -= mi * imp.y; sa[2 * n + b] -= mi * imp.z;
+    sa[3 * n + b] -= da.x; sa[4 * n + b] -= da.y; sa[5 * n + b] -= da.z;
+  }
+}
+
+__device__ __forceinline__ double project(double x, int kind, int row) {   // sparse_iterations_utils.cc:12-21
+  if (kind == KIND_CONTACT) {
+    if (row < 2) { if (x < -1.0) return -1.0; else if (x > 1.0) return 1.0; }
+    else { if (x < 0.0) return 0.0; }
+  }
+  return x;
+}
+
+// One Gauss-Seidel block update: row-by-row substitution inside the 3x3 diagonal block
+// (sparse_iterations_utils.cc:229-236).  x is updated in place; returns delta.
+__device__ __forceinline__ d3 gs_rows(const BlockRec& r, d3 t, double& x0, double& x1, double& x2) {
+  double n0 = project((r.rhs[0] - t.x + r.ddiag[0] * x0) * r.inva[0], r.kind, 0);
+  double d0 = n0 - x0;
+  double n1 = project((r.rhs[1] - (t.y + r.doff[0] * d0) + r.ddiag[1] * x1) * r.inva[1], r.kind, 1);
+  double d1 = n1 - x1;
+  double n2 = project((r.rhs[2] - (t.z + r.doff[1] * d0 + r.doff[2] * d1) + r.ddiag[2] * x2) * r.inva[2], r.kind, 2);
+  double d2 = n2 - x2;
+  x0 = n0; x1 = n1; x2 = n2;
+  return mk3(d0, d1, d2);
+}
+
+// GetResidualError partial sums for one block (sparse_iterations.cc:51-69); the reference
+// classifies with each block's OWN bounds here (ConstructMixedConstraints).
+__device__ __forceinline__ void residual_rows(const BlockRec& r, d3 t, double x0, double x1, double x2, bool eq, double cfm,
+                                              double& se, double& s1, double& s2, double& s3) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const double x = (k == 0) ? x0 : (k == 1 ? x1 : x2);
+    const double wv = get3(t, k) + cfm * x - r.rhs[k];
+    if (eq) { se += wv * wv; continue; }
+    const double lo = (k < 2) ? -1.0 : 0.0;
+    const bool has_hi = (k < 2);
+    if (x == lo && wv < 0) s1 += wv * wv;
+    if (has_hi && x == 1.0 && wv > 0) s2 += wv * wv;
+    if (x > lo && (!has_hi || x < 1.0)) s3 += wv * wv;
+  }
+}
+
+// v' = v + dt (M^-1 f + a); p += dt (v+v')/2; R <- WtoQ((w+w')/2, dt) R  for body b of a world.
+__device__ __forceinline__ bool integrate_body(double* dyn, const double* st, const double* sa, int n, int b, double dt) {
+  const double mi = __ldg(st + b);
+  double Ii[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) Ii[k] = __ldg(st + (1 + k) * n + b);
+  d3 fl = mk3(st[10 * n + b], st[11 * n + b], st[12 * n + b]);
+  d3 ft = mk3(st[13 * n + b], st[14 * n + b], st[15 * n + b]);
+  d3 v = mk3(dyn[12 * n + b], dyn[13 * n + b], dyn[14 * n + b]);
+  d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
+  d3 al = mk3(sa[b], sa[n + b], sa[2 * n + b]);
+  d3 aa = mk3(sa[3 * n + b], sa[4 * n + b], sa[5 * n + b]);
+  d3 vn = v + dt * (fl * mi + al);
+  d3 wn = wv + dt * (mmulv(Ii, ft) + aa);
+  d3 vmid = (v + vn) / 2.0, wmid = (wv + wn) / 2.0;
+  d3 p = mk3(dyn[b], dyn[n + b], dyn[2 * n + b]) + dt * vmid;
+  double wnorm = norm3(wmid);
+  double z2 = dot3(wmid, wmid);
+  d3 axis = (z2 > 0) ? wmid / sqrt(z2) : wmid;
+  double ha = 0.5 * (wnorm * dt);
+  double qw = cos(ha), sn = sin(ha);
+  double qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
+  double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  double Q[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx,
+                 txz - twy, tyz + twx, 1 - (txx + tyy)};
+  double R[9], Rn[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) R[k] = dyn[(3 + k) * n + b];
+  mmulm(Q, R, Rn);
+  dyn[b] = p.x; dyn[n + b] = p.y; dyn[2 * n + b] = p.z;
+#pragma unroll
+  for (int k = 0; k < 9; k++) dyn[(3 + k) * n + b] = Rn[k];
+  dyn[12 * n + b] = vn.x; dyn[13 * n + b] = vn.y; dyn[14 * n + b] = vn.z;
+  dyn[15 * n + b] = wn.x; dyn[16 * n + b] = wn.y; dyn[17 * n + b] = wn.z;
+  double chk = p.x + p.y + p.z + vn.x + vn.y + vn.z + wn.x + wn.y + wn.z;
+  return !(fabs(chk) < 1e300);
+}
+
+// Multipliers / row state of slot `s` in reference row order.
+__device__ __forceinline__ void write_solution(const EggDev& d, int w, const double* recs, const double* lam, int s) {
+  const int nj = d.nj;
+  const double meta = recs[(size_t)s * EGG_REC + REC_META];
+  const int orig = __double2loint(meta);
+  const bool eq = orig < nj;
+  double* lo_out = d.lam_out + (size_t)w * 3 * d.nrec;
+  int* rs_out = d.row_state + (size_t)w * 3 * d.nrec;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double x = __ldcg(lam + 3 * (size_t)s + k);
+    lo_out[3 * orig + k] = x;
+    int state = 0;
+    if (eq) state = 3;
+    else if (x == ((k < 2) ? -1.0 : 0.0)) state = 1;
+    else if (k < 2 && x == 1.0) state = 2;
+    rs_out[3 * orig + k] = state;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant "mw" (default): a warp steps G = 32/LPW worlds in lock-step, LPW lanes per world.
+//
+// ncu on the one-world-per-warp kernels (profiles/r1a_*) showed the solve is bound by the
+// dependent-issue latency of a ~350-instruction stage with ~4 of 32 lanes active (FP64 pipe 11 %,
+// issue slots 30 %, 1.5 warps per scheduler because shared memory capped the CTAs per SM).  This
+// variant packs several worlds into one warp so an instruction serves 4-8x more blocks and
+// relies on many resident warps (not on a prefetch ring) to cover the L2 latency of the record
+// loads; the accumulator a (and optionally M^-1) lives in shared memory.
+template <int LPW, bool MINV_SMEM>
+__global__ void __launch_bounds__(32) egg_pgs_mw_kernel(EggDev d, double dt, int tabcap, int flags) {
+  constexpr int G = 32 / LPW;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
+  constexpr int APW = MINV_SMEM ? 16 : 6;     // doubles per body kept in shared memory
+  double* sa = reinterpret_cast<double*>(smraw) + (size_t)sub * APW * n;
+  double* sminv = sa + 6 * n;
+  unsigned char* tab = smraw + (size_t)G * APW * n * 8 + (size_t)sub * tabcap;   // stage sizes (<= LPW each)
+  const double cfm = d.prm.cfm, tol = d.prm.tol;
+  const int k_max = d.prm.k_max, nj = d.nj;
+
+  for (int wbase = blockIdx.x * G; wbase < d.W; wbase += gridDim.x * G) {
+    const int w = wbase + sub;
+    const bool valid = w < d.W;
+    const int wc = valid ? w : d.W - 1;
+    const double* st = d.stat + (size_t)wc * EGG_STAT * n;
+    const int nc = valid ? nj + d.c_count[wc] : 0;
+    const int ns = valid ? d.n_levels[wc] : 0;
+    const int* gls = d.level_start + (size_t)wc * (d.nrec + 1);
+    const double* recs = d.rec + (size_t)wc * d.nrec * EGG_REC;
+    double* lam = d.lam + (size_t)wc * d.nrec * 3;
+    for (int i = sl; i < 6 * n; i += LPW) sa[i] = 0.0;
+    if (MINV_SMEM)
+      for (int i = sl; i < 10 * n; i += LPW) sminv[i] = st[i];
+    for (int i = sl; i < ns && i < tabcap; i += LPW) tab[i] = (unsigned char)(gls[i + 1] - gls[i]);
+    __syncwarp();
+    const double* minv = MINV_SMEM ? sminv : st;
+    auto stage_cnt = [&](int s) -> int { return (s < tabcap) ? (int)tab[s] : (__ldg(gls + s + 1) - __ldg(gls + s)); };
+
+    int ns_max = ns, nc_max = nc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ns_max = max(ns_max, __shfl_xor_sync(0xffffffffu, ns_max, o));
+      nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, o));
+    }
+    const int nchunk = (nc_max + LPW - 1) / LPW;
+
+    bool active = nc > 0;
+    double err = 0.0;
+    int it = 0;
+    int pass_kind = 0;   // 0: x0 = rhs scatter (sparse_iterations.cc:202), 1: GS update, 2: residual
+    if (__any_sync(0xffffffffu, active)) {
+      while (true) {
+        const int nsteps = (pass_kind == 2) ? nchunk : ns_max;
+        double se = 0, s1 = 0, s2 = 0, s3 = 0;
+        int s0 = 0;                      // first slot of the current stage (update passes)
+        for (int t = 0; t < nsteps; t++) {
+          int slot = -1;
+          if (pass_kind == 2) {
+            const int f = t * LPW + sl;
+            if (active && f < nc) slot = f;
+          } else if (active && t < ns) {
+            const int cnt = stage_cnt(t);
+            if (sl < cnt) slot = s0 + sl;
+            s0 += cnt;
+          }
+          // L1 prefetch of the next step's record (no registers held across the step)
+          if (flags & 1) {
+            int nslot = -1;
+            if (pass_kind == 2) {
+              const int f = (t + 1) * LPW + sl;
+              if (active && f < nc) nslot = f;
+            } else if (active && t + 1 < ns) {
+              if (sl < stage_cnt(t + 1)) nslot = s0 + sl;
+            }
+            if (nslot >= 0) {
+              const char* np = reinterpret_cast<const char*>(recs + (size_t)nslot * EGG_REC);
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(np));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(np + 128));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(lam + 3 * (size_t)nslot));
+            }
+          }
+          if (slot >= 0) {
+            const double2* rp = reinterpret_cast<const double2*>(recs + (size_t)slot * EGG_REC);
+            double2 v[EGG_PIECES];
+#pragma unroll
+            for (int p = 0; p < EGG_PIECES; p++) v[p] = __ldg(rp + p);
+            double* lp = lam + 3 * (size_t)slot;
+            BlockRec r;
+            unpack_rec(v, r);
+            if (pass_kind == 0) {
+              lp[0] = r.rhs[0]; lp[1] = r.rhs[1]; lp[2] = r.rhs[2];
+              block_scatter<!MINV_SMEM>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, minv, n);
+            } else {
+              double c0, c1, c2;
+              if (flags & 2) { c0 = __ldcg(lp); c1 = __ldcg(lp + 1); c2 = __ldcg(lp + 2); }
+              else { c0 = lp[0]; c1 = lp[1]; c2 = lp[2]; }
+              d3 t3 = block_Ja(r, sa, n);
+              if (pass_kind == 1) {
+                d3 dl = gs_rows(r, t3, c0, c1, c2);
+                lp[0] = c0; lp[1] = c1; lp[2] = c2;
+                block_scatter<!MINV_SMEM>(r, dl, sa, minv, n);
+              } else {
+                residual_rows(r, t3, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
+              }
+            }
+          }
+          if (pass_kind != 2) __syncwarp();
+        }
+        if (pass_kind == 2) {
+#pragma unroll
+          for (int o = LPW / 2; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+          }
+          if (active) {
+            err = sqrt(se) + (sqrt(s1) + sqrt(s2) + sqrt(s3));
+            if (!(err > tol && it < k_max)) active = false;
+          }
+          if (!__any_sync(0xffffffffu, active)) break;
+          pass_kind = 1;
+        } else {
+          if (pass_kind == 1 && active) ++it;
+          pass_kind = 2;
+          __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+
+    if (valid) {
+      for (int s = sl; s < nc; s += LPW) write_solution(d, w, recs, lam, s);
+      if (sl == 0) {
+        int* stt = d.stats + (size_t)w * 8;
+        stt[4] = it;
+        stt[5] = 0;
+        stt[6] = (cfm != 0.0);
+        stt[7] = ns;
+        d.resid[w] = err;
+      }
+      double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+      bool bad = false;
+      for (int b = sl; b < n; b += LPW) bad |= integrate_body(dyn, st, sa, n, b, dt);
+      if (bad) atomicOr(&d.status[w], 16 /*EGG_ST_NONFINITE*/);
+    }
+    __syncwarp();
+  }
+}
+
+// Variant "mwpf": as "mw", plus a register double buffer: the next step's record and multipliers
+// are loaded while the current step computes (costs ~100 registers => 9 warps per SM), M^-1 comes
+// through the read-only L1 path.  Fastest measured variant for wide worlds (n = 64).
+template <int LPW>
+__global__ void __launch_bounds__(32) egg_pgs_mwpf_kernel(EggDev d, double dt, int tabcap) {
+  constexpr int G = 32 / LPW;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
+  double* sa = reinterpret_cast<double*>(smraw) + (size_t)sub * 6 * n;
+  unsigned char* tab = smraw + (size_t)G * 6 * n * 8 + (size_t)sub * tabcap;   // stage sizes (<= LPW each)
+  const double cfm = d.prm.cfm, tol = d.prm.tol;
+  const int k_max = d.prm.k_max, nj = d.nj;
+
+  for (int wbase = blockIdx.x * G; wbase < d.W; wbase += gridDim.x * G) {
+    const int w = wbase + sub;
+    const bool valid = w < d.W;
+    const int wc = valid ? w : d.W - 1;
+    const double* st = d.stat + (size_t)wc * EGG_STAT * n;
+    const int nc = valid ? nj + d.c_count[wc] : 0;
+    const int ns = valid ? d.n_levels[wc] : 0;
+    const int* gls = d.level_start + (size_t)wc * (d.nrec + 1);
+    const double* recs = d.rec + (size_t)wc * d.nrec * EGG_REC;
+    double* lam = d.lam + (size_t)wc * d.nrec * 3;
+    for (int i = sl; i < 6 * n; i += LPW) sa[i] = 0.0;
+    for (int i = sl; i < ns && i < tabcap; i += LPW) tab[i] = (unsigned char)(gls[i + 1] - gls[i]);
+    __syncwarp();
+    auto stage_cnt = [&](int s) -> int { return (s < tabcap) ? (int)tab[s] : (__ldg(gls + s + 1) - __ldg(gls + s)); };
+
+    int ns_max = ns, nc_max = nc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ns_max = max(ns_max, __shfl_xor_sync(0xffffffffu, ns_max, o));
+      nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, o));
+    }
+    const int nchunk = (nc_max + LPW - 1) / LPW;
+
+    bool active = nc > 0;
+    double err = 0.0;
+    int it = 0;
+    int pass_kind = 0;   // 0: x0 = rhs scatter (sparse_iterations.cc:202), 1: GS update, 2: residual
+    // record (+ multipliers) of the current step and of the next one (register double buffer)
+    double2 cur[EGG_PIECES], nxt[EGG_PIECES];
+    double c0 = 0, c1 = 0, c2 = 0, p0 = 0, p1 = 0, p2 = 0;
+    int cur_slot = -1, nxt_slot = -1;
+    // stage cursor of the update passes
+    int s0_next = 0;     // first slot of the stage that will be fetched next
+    auto fetch = [&](int slot, bool with_lam) {
+      nxt_slot = slot;
+      if (slot >= 0) {
+        const double2* rp = reinterpret_cast<const double2*>(recs + (size_t)slot * EGG_REC);
+#pragma unroll
+        for (int p = 0; p < EGG_PIECES; p++) nxt[p] = __ldg(rp + p);
+        if (with_lam) {
+          p0 = __ldcg(lam + 3 * (size_t)slot); p1 = __ldcg(lam + 3 * (size_t)slot + 1); p2 = __ldcg(lam + 3 * (size_t)slot + 2);
+        }
+      }
+    };
+    auto stage_slot = [&](int s) -> int {     // slot of this lane in stage s (call with s in order)
+      if (!active || s >= ns) return -1;
+      const int cnt = stage_cnt(s);
+      const int mine = (sl < cnt) ? s0_next + sl : -1;
+      s0_next += cnt;
+      return mine;
+    };
+    auto chunk_slot = [&](int k) -> int {
+      const int f = k * LPW + sl;
+      return (active && f < nc) ? f : -1;
+    };
+
+    if (__any_sync(0xffffffffu, active)) {
+      s0_next = 0;
+      fetch(stage_slot(0), false);
+      while (true) {
+        const int nsteps = (pass_kind == 2) ? nchunk : ns_max;
+        double se = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int t = 0; t < nsteps; t++) {
+          // rotate the double buffer, then prefetch step t+1 (or step 0 of the next pass)
+#pragma unroll
+          for (int p = 0; p < EGG_PIECES; p++) cur[p] = nxt[p];
+          cur_slot = nxt_slot; c0 = p0; c1 = p1; c2 = p2;
+          const bool last = (t + 1 == nsteps);
+          if (!last) {
+            fetch(pass_kind == 2 ? chunk_slot(t + 1) : stage_slot(t + 1), pass_kind != 0);
+          } else if (pass_kind == 2) {
+            s0_next = 0;
+            fetch(stage_slot(0), true);       // residual never writes lam: safe to prefetch
+          } else {
+            fetch(chunk_slot(0), false);      // lam of chunk 0 may still be in flight: read it later
+          }
+          if (cur_slot >= 0) {
+            BlockRec r;
+            unpack_rec(cur, r);
+            double* lp = lam + 3 * (size_t)cur_slot;
+            if (pass_kind == 0) {
+              lp[0] = r.rhs[0]; lp[1] = r.rhs[1]; lp[2] = r.rhs[2];
+              block_scatter<true>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, st, n);
+            } else if (pass_kind == 1) {
+              d3 t3 = block_Ja(r, sa, n);
+              d3 dl = gs_rows(r, t3, c0, c1, c2);
+              lp[0] = c0; lp[1] = c1; lp[2] = c2;
+              block_scatter<true>(r, dl, sa, st, n);
+            } else {
+              d3 t3 = block_Ja(r, sa, n);
+              residual_rows(r, t3, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
+            }
+          }
+          __syncwarp();
+          if (last && pass_kind != 2 && nxt_slot >= 0) {
+            // first residual chunk: its multipliers were written during the pass that just ended
+            p0 = __ldcg(lam + 3 * (size_t)nxt_slot); p1 = __ldcg(lam + 3 * (size_t)nxt_slot + 1); p2 = __ldcg(lam + 3 * (size_t)nxt_slot + 2);
+          }
+        }
+        if (pass_kind == 2) {
+#pragma unroll
+          for (int o = LPW / 2; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+          }
+          if (active) {
+            err = sqrt(se) + (sqrt(s1) + sqrt(s2) + sqrt(s3));
+            if (!(err > tol && it < k_max)) active = false;
+          }
+          if (!__any_sync(0xffffffffu, active)) break;
+          if (!active) nxt_slot = -1;          // this world dropped out: discard its prefetch
+          pass_kind = 1;
+        } else {
+          if (pass_kind == 1 && active) ++it;
+          pass_kind = 2;
+        }
+      }
+    }
+    __syncwarp();
+
+    if (valid) {
+      for (int s = sl; s < nc; s += LPW) write_solution(d, w, recs, lam, s);
+      if (sl == 0) {
+        int* stt = d.stats + (size_t)w * 8;
+        stt[4] = it;
+        stt[5] = 0;
+        stt[6] = (cfm != 0.0);
+        stt[7] = ns;
+        d.resid[w] = err;
+      }
+      double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+      bool bad = false;
+      for (int b = sl; b < n; b += LPW) bad |= integrate_body(dyn, st, sa, n, b, dt);
+      if (bad) atomicOr(&d.status[w], 16 /*EGG_ST_NONFINITE*/);
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant "tma": one world per warp, a stage's records staged through a shared-memory ring by
+// TMA bulk copies (cp.async.bulk + mbarrier complete_tx).  Kept selectable (EGG_PGS_VARIANT=tma)
+// as the measured alternative; see profiles/r1a_pgs_tma_ring_summary.txt.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+
+constexpr int TMA_NSTAGE = 3;                       // ring depth: NSTAGE-1 stages of lookahead
+constexpr int TMA_CAP = 8;                          // blocks per stage (240-byte stride is conflict-free for <= 8 lanes)
+constexpr int TMA_SLOT_BYTES = TMA_CAP * EGG_REC * 8;
+constexpr int TMA_LS_CAP = 1023;
+
+// Shared memory per CTA (one warp): a[6n] | minv[10n] | ring | mbar | stage starts
+__global__ void __launch_bounds__(32) egg_pgs_tma_kernel(EggDev d, double dt) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = d.n, lane = threadIdx.x;
+  double* sa = reinterpret_cast<double*>(smraw);
+  double* sminv = sa + 6 * n;
+  unsigned char* ring = smraw + (((size_t)16 * n * 8 + 127) & ~(size_t)127);
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)TMA_NSTAGE * TMA_SLOT_BYTES);
+  int* sls = reinterpret_cast<int*>(mbar + TMA_NSTAGE);
+  const double cfm = d.prm.cfm, tol = d.prm.tol;
+  const int k_max = d.prm.k_max;
+  const int nj = d.nj;
+
+  if (lane == 0) {
+    for (int k = 0; k < TMA_NSTAGE; k++) mbar_init(&mbar[k], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  unsigned issued = 0, consumed = 0;   // warp-uniform monotonic stage counters (slot / parity)
+
+  for (int w = blockIdx.x; w < d.W; w += gridDim.x) {
+    const double* st = d.stat + (size_t)w * EGG_STAT * n;
+    for (int i = lane; i < 10 * n; i += 32) sminv[i] = st[i];
+    for (int i = lane; i < 6 * n; i += 32) sa[i] = 0.0;
+    const int nc = nj + d.c_count[w];
+    const int ns = d.n_levels[w];
+    const int* gls = d.level_start + (size_t)w * (d.nrec + 1);
+    for (int i = lane; i <= ns && i <= TMA_LS_CAP; i += 32) sls[i] = gls[i];
+    const double* recs = d.rec + (size_t)w * d.nrec * EGG_REC;
+    double* lam = d.lam + (size_t)w * d.nrec * 3;
+    __syncwarp();
+    auto stage_start = [&](int s) -> int { return (s <= TMA_LS_CAP) ? sls[s] : __ldg(gls + s); };
+
+    unsigned q_issue = 0;
+    auto issue = [&]() {                        // counters are warp-uniform; lane 0 talks to the TMA
+      if (lane == 0) {
+        const int s = (int)(q_issue % (unsigned)ns);
+        const int s0 = stage_start(s), cnt = stage_start(s + 1) - s0;
+        const unsigned slot = issued % TMA_NSTAGE;
+        const unsigned bytes = (unsigned)cnt * EGG_REC * 8;
+        mbar_expect_tx(&mbar[slot], bytes);
+        tma_bulk_g2s(ring + (size_t)slot * TMA_SLOT_BYTES, recs + (size_t)s0 * EGG_REC, bytes, &mbar[slot]);
+      }
+      issued++;
+      q_issue++;
+    };
+    double err = 0.0;
+    int it = 0;
+    if (nc > 0) {
+      for (int k = 0; k < TMA_NSTAGE - 1; k++) issue();
+      __syncwarp();
+      int pass_kind = 0;
+      bool done = false;
+      double c0 = 0, c1 = 0, c2 = 0;
+      while (!done) {
+        double se = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int s = 0; s < ns; s++) {
+          issue();   // refills the slot consumed by the previous stage (all lanes passed its __syncwarp)
+          const unsigned slot = consumed % TMA_NSTAGE, parity = (consumed / TMA_NSTAGE) & 1u;
+          while (!mbar_try_wait(&mbar[slot], parity)) {}
+          consumed++;
+          const int s0 = stage_start(s), cnt = stage_start(s + 1) - s0;
+          const int sn = (s + 1 == ns) ? 0 : s + 1;
+          const int s0n = stage_start(sn), cntn = stage_start(sn + 1) - s0n;
+          double p0 = 0, p1 = 0, p2 = 0;
+          if (ns > 1 && lane < cntn) {
+            const double* pq = lam + 3 * (size_t)(s0n + lane);
+            p0 = __ldcg(pq); p1 = __ldcg(pq + 1); p2 = __ldcg(pq + 2);
+          }
+          if (lane < cnt) {
+            BlockRec r;
+            unpack_rec(reinterpret_cast<const double2*>(ring + (size_t)slot * TMA_SLOT_BYTES) + lane * EGG_PIECES, r);
+            double* lp = lam + 3 * (size_t)(s0 + lane);
+            if (ns == 1 && pass_kind != 0) { c0 = __ldcg(lp); c1 = __ldcg(lp + 1); c2 = __ldcg(lp + 2); }
+            if (pass_kind == 0) {
+              lp[0] = r.rhs[0]; lp[1] = r.rhs[1]; lp[2] = r.rhs[2];
+              block_scatter<false>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, sminv, n);
+            } else if (pass_kind == 1) {
+              d3 t = block_Ja(r, sa, n);
+              d3 dl = gs_rows(r, t, c0, c1, c2);
+              lp[0] = c0; lp[1] = c1; lp[2] = c2;
+              block_scatter<false>(r, dl, sa, sminv, n);
+            } else {
+              d3 t = block_Ja(r, sa, n);
+              residual_rows(r, t, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
+            }
+          }
+          c0 = p0; c1 = p1; c2 = p2;
+          __syncwarp();
+        }
+        if (pass_kind == 2) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+          }
+          err = sqrt(se) + (sqrt(s1) + sqrt(s2) + sqrt(s3));
+          if (err > tol && it < k_max) pass_kind = 1; else done = true;
+        } else {
+          if (pass_kind == 1) ++it;
+          pass_kind = 2;
+        }
+      }
+      while (consumed != issued) {   // drain the lookahead before the ring is reused
+        const unsigned slot = consumed % TMA_NSTAGE, parity = (consumed / TMA_NSTAGE) & 1u;
+        while (!mbar_try_wait(&mbar[slot], parity)) {}
+        consumed++;
+      }
+      __syncwarp();
+    }
+    for (int s = lane; s < nc; s += 32) write_solution(d, w, recs, lam, s);
+    if (lane == 0) {
+      int* stt = d.stats + (size_t)w * 8;
+      stt[4] = it;
+      stt[5] = 0;
+      stt[6] = (cfm != 0.0);
+      stt[7] = ns;
+      d.resid[w] = err;
+    }
+    double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+    bool bad = false;
+    for (int b = lane; b < n; b += 32) bad |= integrate_body(dyn, st, sa, n, b, dt);
+    if (__any_sync(0xffffffffu, bad) && lane == 0) d.status[w] |= 16 /*EGG_ST_NONFINITE*/;
+    __syncwarp();
+  }
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+bool use_tma_variant() {
+  const char* e = getenv("EGG_PGS_VARIANT");
+  return e && e[0] == 't';
+}
+// Register-prefetch variant: default for wide worlds, EGG_PGS_VARIANT=mw / mwpf overrides.
+bool use_pf_variant(const EggDev& d) {
+  const char* e = getenv("EGG_PGS_VARIANT");
+  if (e && e[0] == 'm') return e[1] == 'w' && e[2] == 'p';
+  return d.n > 24;
+}
+
+template <int LPW, bool MINV_SMEM>
+void launch_mw2(const EggDev& d, double dt, cudaStream_t s) {
+  constexpr int G = 32 / LPW;
+  int tabcap = d.nrec + 1;
+  if (tabcap > 2048) tabcap = 2048;
+  tabcap = (tabcap + 15) & ~15;
+  size_t smem = (size_t)G * (MINV_SMEM ? 16 : 6) * d.n * 8 + (size_t)G * tabcap;
+  cudaFuncSetAttribute(egg_pgs_mw_kernel<LPW, MINV_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 16);
+  int groups = (d.W + G - 1) / G;
+  int grid = groups < num_sms() * per_sm ? groups : num_sms() * per_sm;
+  egg_pgs_mw_kernel<LPW, MINV_SMEM><<<grid, 32, smem, s>>>(d, dt, tabcap, env_int("EGG_PGS_FLAGS", 0));
+}
+template <int LPW>
+void launch_mwpf(const EggDev& d, double dt, cudaStream_t s) {
+  constexpr int G = 32 / LPW;
+  int tabcap = d.nrec + 1;
+  if (tabcap > 2048) tabcap = 2048;
+  tabcap = (tabcap + 15) & ~15;
+  size_t smem = (size_t)G * 6 * d.n * 8 + (size_t)G * tabcap;
+  cudaFuncSetAttribute(egg_pgs_mwpf_kernel<LPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 9);
+  int groups = (d.W + G - 1) / G;
+  int grid = groups < num_sms() * per_sm ? groups : num_sms() * per_sm;
+  egg_pgs_mwpf_kernel<LPW><<<grid, 32, smem, s>>>(d, dt, tabcap);
+}
+template <int LPW>
+void launch_mw(const EggDev& d, double dt, cudaStream_t s) {
+  // M^-1 in shared memory when the per-warp footprint still allows >= 8 warps per SM.
+  constexpr int G = 32 / LPW;
+  const bool minv_smem = env_int("EGG_PGS_MINV_SMEM", 1) != 0;
+  if (minv_smem) launch_mw2<LPW, true>(d, dt, s);
+  else launch_mw2<LPW, false>(d, dt, s);
+}
+
+}  // namespace
+
+// Lanes per world of the default solver = maximum blocks per stage the assembly may emit.
+int egg_stage_cap(const EggDev& d) {
+  if (use_tma_variant()) return TMA_CAP;
+  int lpw = env_int("EGG_PGS_LPW", 0);
+  if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16 && lpw != 32) lpw = 8;
+  if (use_pf_variant(d) && lpw != 4) lpw = 8;
+  return lpw;
+}
+
+void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s) {
+  size_t smem = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double) + (size_t)(7 * d.nrec + d.n + 8) * sizeof(int);
+  const int cap = egg_stage_cap(d);
+  if (d.nrec <= 128) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_assemble_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_assemble_kernel<64><<<d.W, 64, smem, s>>>(d, dt, cap);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_assemble_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_assemble_kernel<256><<<d.W, 256, smem, s>>>(d, dt, cap);
+  }
+}
+
+void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) {
+  if (use_tma_variant()) {
+    size_t smem = (((size_t)16 * d.n * 8 + 127) & ~(size_t)127) + (size_t)TMA_NSTAGE * TMA_SLOT_BYTES + TMA_NSTAGE * 8 + (size_t)(TMA_LS_CAP + 1) * 4;
+    cudaFuncSetAttribute(egg_pgs_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 12);
+    int grid = d.W < num_sms() * per_sm ? d.W : num_sms() * per_sm;
+    egg_pgs_tma_kernel<<<grid, 32, smem, s>>>(d, dt);
+    return;
+  }
+  if (use_pf_variant(d)) {
+    if (egg_stage_cap(d) == 4) launch_mwpf<4>(d, dt, s);
+    else launch_mwpf<8>(d, dt, s);
+    return;
+  }
+  switch (egg_stage_cap(d)) {
+    case 1: launch_mw<1>(d, dt, s); break;
+    case 2: launch_mw<2>(d, dt, s); break;
+    case 4: launch_mw<4>(d, dt, s); break;
+    case 8: launch_mw<8>(d, dt, s); break;
+    case 16: launch_mw<16>(d, dt, s); break;
+    default: launch_mw<32>(d, dt, s); break;
+  }
+}

@@ -108,6 +108,12 @@ int egg_init(egg_batch* b);
  * the batch stream. */
 int egg_step(egg_batch* b, double dt, int integrator, int n_steps);
 
+/* Device-side copy of the dynamic Body state (p,R,v,w of every world): egg_snapshot saves it,
+ * egg_restore puts it back (asynchronous on the batch stream).  Used to replay a step from the
+ * same state (stepwise parity, stationary benchmarks, MPC rollouts from a common start). */
+int egg_snapshot(egg_batch* b);
+int egg_restore(egg_batch* b);
+
 /* Reads back Body state (body.h:50-58 accessors); synchronises the stream. */
 int egg_get_bodies(egg_batch* b, double* p, double* R, double* v, double* w);
 
@@ -143,6 +149,17 @@ int egg_capacity(const egg_batch* b);
 /* Bytes of device memory held by the batch; number of kernel launches issued so far. */
 long long egg_device_bytes(const egg_batch* b);
 long long egg_launch_count(const egg_batch* b);
+
+/* Per-kernel device time.  With profiling on, egg_step brackets each of its kernels with CUDA
+ * events on the batch stream; egg_get_kernel_ms synchronises and returns the milliseconds
+ * accumulated since the last call: out[0] narrowphase, out[1] row assembly, out[2] solve +
+ * integrate, out[3] = number of steps counted. */
+int egg_set_profiling(egg_batch* b, int on);
+int egg_get_kernel_ms(egg_batch* b, double* out4);
+
+/* FP64 roofline denominator: a dependent-free DFMA loop on every SM of `device`; returns TFLOP/s
+ * (2 flop per FMA), or a negative egg_error. */
+double egg_fp64_peak_tflops(int device);
 
 /* Pinned host staging (cudaHostAlloc) for end-to-end measurements. */
 void* egg_host_alloc(long long bytes);
