@@ -63,3 +63,111 @@ def test_legged_pgs_joints_and_contacts():
     scene = E.scenes.legged20(4, seed=5000)
     worst = _stepwise(scene, 3, list(range(4)), dict(solver=E.SOLVER_PGS, k_max=100), dict(solver=1, k_max=100))
     print("legged worst", worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# Against the committed golden fixtures (tests/golden/*.npz).
+def _vs_golden(name, scene, nw, ns, batch_kw, tol=1e-9):
+    import os
+    import eggshell_b200 as E
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    b = E.scenes.make_batch(scene, taps=True, **batch_kw)
+    for s in range(ns):
+        # replay from the golden state of the previous step so that chaos cannot accumulate
+        if s > 0:
+            b.set_state(*[np.stack([g[f"w{wi}_s{s-1}_{k}"] for wi in range(nw)]) for k in ("p", "R", "v", "w")])
+        b.step(scene["dt"])
+        p, R, v, w = b.bodies()
+        con = b.contacts()
+        st = b.status()
+        ph = b.pair_hits()
+        for wi in range(nw):
+            pre = f"w{wi}_s{s}_"
+            nc = int(g[pre + "stats"][1])
+            assert con["count"][wi] == nc
+            assert st["n_contacts_raw"][wi] == g[pre + "stats"][0] and st["n_pair_hits"][wi] == g[pre + "stats"][3]
+            assert st["sweeps"][wi] == g[pre + "stats"][4]
+            assert np.array_equal(con["i0"][wi, :nc], g[pre + "c_i0"]) and np.array_equal(con["i1"][wi, :nc], g[pre + "c_i1"])
+            assert np.array_equal(con["code"][wi, :nc], g[pre + "c_code"])
+            nh = int(ph["n"][wi])
+            assert np.array_equal(ph["i"][wi, :nh], g[pre + "hit_i"]) and np.array_equal(ph["j"][wi, :nh], g[pre + "hit_j"])
+            assert np.array_equal(ph["code"][wi, :nh], g[pre + "hit_code"]) and np.array_equal(ph["count"][wi, :nh], g[pre + "hit_count"])
+            nr = len(g[pre + "lam"])
+            assert np.array_equal(con["row_state"][wi, :nr], g[pre + "row_state"])
+            for key, val in (("p", p[wi]), ("R", R[wi]), ("v", v[wi]), ("w", w[wi]), ("c_pos", con["pos"][wi, :nc]),
+                             ("c_nrm", con["nrm"][wi, :nc]), ("c_depth", con["depth"][wi, :nc])):
+                assert rel_err(val, g[pre + key]) <= tol, (name, wi, s, key, rel_err(val, g[pre + key]))
+            assert rel_err(con["lam"][wi, :nr], g[pre + "lam"]) <= 1e-7
+    b.close()
+
+
+def test_golden_fixtures_pgs():
+    import eggshell_b200 as E
+    S = E.scenes
+    _vs_golden("stack10_pgs", S.stack10(2, seed=1000), 2, 2, dict(solver=E.SOLVER_PGS))
+    _vs_golden("pile64_pgs_k50", S.pile64(1, seed=3000), 1, 2, dict(solver=E.SOLVER_PGS, k_max=50))
+    _vs_golden("legged20_pgs_k100", S.legged20(2, seed=5000), 2, 2, dict(solver=E.SOLVER_PGS, k_max=100))
+    _vs_golden("chain32_pgs_k100", S.chain32(1, seed=4000), 1, 2, dict(solver=E.SOLVER_PGS, k_max=100))
+    _vs_golden("cairn4_pgs", S.cairn(2, rocks=4, zb=(0.2, 0.6), seed=11), 2, 5, dict(solver=E.SOLVER_PGS))
+
+
+# ---------------------------------------------------------------------------------------------
+# Full BASELINE sizes: size-independent properties.
+def test_full_size_c2_properties():
+    """4096 worlds x 10-box stack: a world's result does not depend on the batch around it, a
+    replay from the snapshot is bit-identical, and the contact list is in reference order."""
+    import eggshell_b200 as E
+    W = 4096
+    scene = E.scenes.stack10(W, seed=1000)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=30, taps=False)
+    b.snapshot()
+    b.step(scene["dt"])
+    out1 = [x.copy() for x in b.bodies()]
+    con = b.contacts()
+    st = b.status()
+    assert int(st["status"].max()) == 0
+    b.restore()
+    b.step(scene["dt"])
+    out2 = b.bodies()
+    for a, c in zip(out1, out2):
+        assert np.array_equal(a, c)                       # deterministic replay
+    # order: ground contacts (i0 = -1) by body, then pairs lexicographic (ensembles.cc:449-473)
+    for wi in (0, 1, 17, W - 1):
+        nc = con["count"][wi]
+        key = con["i0"][wi, :nc].astype(np.int64) * 1000 + con["i1"][wi, :nc]
+        assert np.all(np.diff(key) >= 0)
+        assert np.all(con["depth"][wi, :nc] >= -1e-9)
+    # independence: worlds 5..8 alone give the same bits
+    sub = {k: (v[5:9] if isinstance(v, np.ndarray) and v.shape[:1] == (W,) else v) for k, v in scene.items()}
+    sub["W"] = 4
+    b2 = E.scenes.make_batch(sub, solver=E.SOLVER_PGS, k_max=30)
+    b2.step(scene["dt"])
+    for a, c in zip(out1, b2.bodies()):
+        assert np.array_equal(a[5:9], c)
+    # spot-check 3 worlds of the big batch against the oracle
+    idx = [0, 2047, W - 1]
+    ows = [oracle_world(scene, wi, solver=1, k_max=30)[0] for wi in idx]
+    for ow in ows:
+        ow.step(scene["dt"])
+    compare_step(b, ows, idx)
+    b.close(); b2.close()
+
+
+def test_full_size_c3_contact_counts_and_capacity():
+    """65536 worlds x 64-body pile, one step at k_max = 3: no overflow / non-finite status, contact
+    statistics in the expected band, and sampled worlds bit-exact vs the oracle."""
+    import eggshell_b200 as E
+    W = 65536
+    scene = E.scenes.pile64(W, seed=3000)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=3, max_contacts=1024)
+    b.step(scene["dt"])
+    st = b.status()
+    assert int(np.bitwise_or.reduce(st["status"])) == 0
+    assert 400 < st["n_contacts"].mean() < 600 and st["n_contacts"].max() <= 1024
+    assert 200 < st["n_pair_hits"].mean() < 320
+    idx = [0, 31337, W - 1]
+    ows = [oracle_world(scene, wi, solver=1, k_max=3)[0] for wi in idx]
+    for ow in ows:
+        ow.step(scene["dt"])
+    compare_step(b, ows, idx)
+    b.close()
