@@ -22,7 +22,7 @@ ST_LCP_FAILED, ST_JOINT_CONFLICT, ST_BAD_INIT, ST_CONTACT_OVERFLOW, ST_NONFINITE
 
 EXPORTS = [
     "egg_desc_default", "egg_create", "egg_destroy", "egg_set_bodies", "egg_set_state", "egg_set_joints",
-    "egg_set_external", "egg_init", "egg_step", "egg_snapshot", "egg_restore", "egg_get_bodies", "egg_get_contacts", "egg_get_pair_hits",
+    "egg_set_external", "egg_init", "egg_step", "egg_snapshot", "egg_restore", "egg_update_contacts", "egg_get_static", "egg_get_bodies", "egg_get_contacts", "egg_get_pair_hits",
     "egg_get_status", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
     "egg_launch_count", "egg_capacity", "egg_set_profiling", "egg_get_kernel_ms", "egg_fp64_peak_tflops", "egg_host_alloc", "egg_host_free", "egg_last_error", "egg_version",
 ]
@@ -164,6 +164,15 @@ class Batch:
     # -- stepping -----------------------------------------------------------------------------
     def step(self, dt, n_steps=1, integrator=OPEN_DYNAMICS_ENGINE):
         _chk(lib().egg_step(self.h, C.c_double(dt), int(integrator), int(n_steps)), "egg_step")
+
+    def update_contacts(self):
+        _chk(lib().egg_update_contacts(self.h), "egg_update_contacts")
+
+    def static(self):
+        W, n = self.W, self.n
+        ml, ma, f = np.empty((W, n)), np.empty((W, n, 3, 3)), np.empty((W, n, 6))
+        _chk(lib().egg_get_static(self.h, _p(ml), _p(ma), _p(f)), "egg_get_static")
+        return ml, ma, f
 
     def snapshot(self):
         _chk(lib().egg_snapshot(self.h), "egg_snapshot")

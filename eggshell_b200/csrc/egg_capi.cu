@@ -337,7 +337,7 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     return EGG_ERR_UNSUPPORTED;
   }
   const int solver = b->dev.prm.solver;
-  if (solver != EGG_SOLVER_PGS && solver != EGG_SOLVER_DENSE_MURTY) {
+  if (solver != EGG_SOLVER_PGS && solver != EGG_SOLVER_DENSE_MURTY) {  // Jacobi / SOR: not on the device yet
     g_err = "solver not implemented on the device yet";
     return EGG_ERR_UNSUPPORTED;
   }
@@ -362,6 +362,26 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     b->launches += 3;
   }
   CK(cudaGetLastError());
+  return EGG_OK;
+}
+
+int egg_update_contacts(egg_batch* b) {
+  if (!b) return EGG_ERR_ARG;
+  if (!b->initialised) { g_err = "egg_update_contacts before egg_init"; return EGG_ERR_STATE; }
+  CK(cudaSetDevice(b->device));
+  egg_launch_collide(b->dev, b->stream);
+  b->launches++;
+  CK(cudaGetLastError());
+  return EGG_OK;
+}
+
+int egg_get_static(egg_batch* b, double* minv_lin, double* minv_ang, double* f_ext) {
+  if (!b) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const int n = b->dev.n;
+  if (minv_lin) RET(download(b, minv_lin, n, 1, b->dev.stat, EGG_STAT, 0));
+  if (minv_ang) RET(download(b, minv_ang, n, 9, b->dev.stat, EGG_STAT, 1));
+  if (f_ext) RET(download(b, f_ext, n, 6, b->dev.stat, EGG_STAT, 10));
   return EGG_OK;
 }
 

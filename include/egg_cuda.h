@@ -58,7 +58,8 @@ enum egg_status {
   EGG_ST_JOINT_CONFLICT = 2,    /* ensembles.cc:280-285 would Panic */
   EGG_ST_BAD_INIT = 4,          /* ensembles.cc:27 CHECK_MSG would fail */
   EGG_ST_CONTACT_OVERFLOW = 8,  /* more contacts than max_contacts; the tail was dropped */
-  EGG_ST_NONFINITE = 16         /* NaN/Inf reached the state */
+  EGG_ST_NONFINITE = 16,        /* NaN/Inf reached the state */
+  EGG_ST_DENSE_OVERFLOW = 32    /* more rows than the dense path is provisioned for; lambda = 0 */
 };
 
 /* Compile-time constants of the reference gathered into one POD (SURVEY.md §5 "Config"):
@@ -107,6 +108,15 @@ int egg_init(egg_batch* b);
 /* n_steps x Ensemble::Step(dt, integrator) (ensembles.cc:390-427) on every world; asynchronous on
  * the batch stream. */
 int egg_step(egg_batch* b, double dt, int integrator, int n_steps);
+
+/* Ensemble::UpdateContacts + CheckAndCorrectEnsembleState only (ensembles.cc:445-480, 241-329):
+ * runs the narrowphase kernel on the current state without stepping; read the result with
+ * egg_get_contacts / egg_get_pair_hits. */
+int egg_update_contacts(egg_batch* b);
+
+/* Ensemble::M_inverse() / external_force_torque_ taps (ensembles.h:68,88-89) as frozen by egg_init:
+ * minv_lin [W][n], minv_ang [W][n][9], f_ext [W][n][6].  Any pointer may be NULL. */
+int egg_get_static(egg_batch* b, double* minv_lin, double* minv_ang, double* f_ext);
 
 /* Device-side copy of the dynamic Body state (p,R,v,w of every world): egg_snapshot saves it,
  * egg_restore puts it back (asynchronous on the batch stream).  Used to replay a step from the

@@ -165,9 +165,117 @@ def test_full_size_c3_contact_counts_and_capacity():
     assert int(np.bitwise_or.reduce(st["status"])) == 0
     assert 400 < st["n_contacts"].mean() < 600 and st["n_contacts"].max() <= 1024
     assert 200 < st["n_pair_hits"].mean() < 320
+    # sampled worlds: re-run them alone (bit-identical to their slice of the big batch) and check
+    # that small batch against the oracle, contacts included
     idx = [0, 31337, W - 1]
+    p, R, v, w = b.bodies()
+    sub = {k: (val[idx] if isinstance(val, np.ndarray) and val.shape[:1] == (W,) else val) for k, val in scene.items()}
+    sub["W"] = len(idx)
+    b2 = E.scenes.make_batch(sub, solver=E.SOLVER_PGS, k_max=3, max_contacts=1024, taps=True)
+    b2.step(scene["dt"])
+    for big, small in zip((p, R, v, w), b2.bodies()):
+        assert np.array_equal(big[idx], small)
     ows = [oracle_world(scene, wi, solver=1, k_max=3)[0] for wi in idx]
     for ow in ows:
         ow.step(scene["dt"])
-    compare_step(b, ows, idx)
+    compare_step(b2, ows, list(range(len(idx))))
+    b.close(); b2.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Dense path (what the reference ships): Schur complement + Murty principal pivoting.
+def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-6, **kw):
+    import eggshell_b200 as E
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_DENSE_MURTY, taps=True, **kw)
+    ows = [oracle_world(scene, wi, solver=0)[0] for wi in worlds_idx]
+    dt = scene["dt"]
+    npiv = 0
+    for s in range(nsteps):
+        p, R, v, w = b.bodies()
+        for k, wi in enumerate(worlds_idx):
+            ows[k].set_state(p[wi], R[wi], v[wi], w[wi])
+        b.step(dt)
+        for ow in ows:
+            ow.step(dt)
+        worst = compare_step(b, ows, worlds_idx, tol=tol)
+        st = b.status()
+        con = b.contacts()
+        for k, wi in enumerate(worlds_idx):
+            os_ = ows[k].stats()
+            assert st["pivots"][wi] == os_["pivots"], f"step {s} world {wi}: Murty pivots {st['pivots'][wi]} != {os_['pivots']}"
+            assert st["cfm_applied"][wi] == os_["cfm_applied"], f"step {s} world {wi}: cfm decision differs"
+            assert (st["status"][wi] & 1) == (os_["status"] & 1)
+            lam, rhs, rs = ows[k].solution()
+            assert np.array_equal(con["row_state"][wi, :len(rs)], rs), f"step {s} world {wi}: active set differs"
+            npiv += os_["pivots"]
+        assert worst["lam"] <= lam_tol, f"lambda mismatch {worst['lam']:.3e}"
     b.close()
+    return npiv
+
+
+def test_dense_chain10_golden():
+    """C1: Chain(10,(2,2,1)) with the reference's default dense solver against the golden file,
+    including steps around 400 where the chain hits the ground (contacts, cfm on, ~30 pivots)."""
+    import os
+    import eggshell_b200 as E
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "chain10_dense.npz"))
+    scene = E.scenes.chain(1, links=10, anchor=(2.0, 2.0, 1.0))
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_DENSE_MURTY)
+    # free swing: 2 steps from the initial state
+    for s in (1, 2):
+        b.step(0.001)
+        p, R, v, w = b.bodies()
+        for key, val in (("p", p[0]), ("R", R[0]), ("v", v[0]), ("w", w[0])):
+            assert rel_err(val, g[f"s{s}_{key}"]) <= 1e-9, (s, key)
+        st = b.status()
+        assert [st["n_contacts_raw"][0], st["n_contacts"][0], st["n_rows"][0], st["n_pair_hits"][0]] == g[f"s{s}_stats"][:4].tolist()
+    # contact phase: replay golden states 399 -> 400 -> 401
+    for s in (400, 401):
+        b.set_state(*[g[f"s{s-1}_{k}"][None] for k in ("p", "R", "v", "w")])
+        b.step(0.001)
+        p, R, v, w = b.bodies()
+        st = b.status()
+        con = b.contacts()
+        gs = g[f"s{s}_stats"]
+        assert [st["n_contacts_raw"][0], st["n_contacts"][0], st["n_rows"][0], st["n_pair_hits"][0]] == gs[:4].tolist()
+        assert st["pivots"][0] == gs[5] and st["cfm_applied"][0] == gs[6] and st["status"][0] == gs[7]
+        nr = len(g[f"s{s}_lam"])
+        assert np.array_equal(con["row_state"][0, :nr], g[f"s{s}_row_state"])
+        for key, val in (("p", p[0]), ("R", R[0]), ("v", v[0]), ("w", w[0])):
+            assert rel_err(val, g[f"s{s}_{key}"]) <= 1e-9, (s, key)
+        assert rel_err(con["lam"][0, :nr], g[f"s{s}_lam"]) <= 1e-6
+    b.close()
+
+
+def test_dense_cairn_and_chain_stepwise():
+    import eggshell_b200 as E
+    npiv = _stepwise_dense(E.scenes.cairn(8, rocks=4, zb=(0.2, 0.5), seed=21), 25, list(range(8)))
+    assert npiv > 0
+    _stepwise_dense(E.scenes.chain(2, links=6, anchor=(0.0, 0.0, 0.25), seed=5, anchor_jitter=0.05), 6, [0, 1])
+
+
+def test_cpp_host_mirror_demo():
+    """The C++ mirror of model.h / ensembles.h (include/eggshell, eggshell_b200/host): the headless
+    driver runs SimulationInitialization() + 25 x SimulationStep() (model.cc:33-71) and its hanging
+    chain must match the oracle's Chain(10,(2,2,1)) after 25 dense steps."""
+    import os
+    import subprocess
+    from oracle import pyoracle as O
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "eggshell_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s"])
+    out = subprocess.run([os.path.join(host, "host_demo"), "25"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    i = lines.index("chain 10")
+    got = np.array([[float(x) for x in ln.split()[1:]] for ln in lines[i + 1:i + 11]])
+    W = O.World()
+    W.build_chain(10, [2, 2, 1])
+    W.set_params(solver=O.SOLVER_DENSE_MURTY)
+    assert W.init() == 0
+    for _ in range(25):
+        W.step(0.001)
+    p, R, v, w = W.bodies()
+    assert rel_err(got[:, :3], p) <= 1e-9 and rel_err(got[:, 3:], v, floor=1e-3) <= 1e-6
+    j = lines.index("cairn 4")
+    cairn = np.array([[float(x) for x in ln.split()[1:]] for ln in lines[j + 1:j + 5]])
+    assert np.all(cairn[:, 5] < 0)      # the rocks are falling
