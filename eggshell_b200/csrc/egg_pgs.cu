@@ -256,47 +256,67 @@ __device__ __forceinline__ void unpack_rec(const double2* v, BlockRec& r) {
   r.orig = __double2loint(f[REC_META]); r.kind = __double2hiint(f[REC_META]);
 }
 
+// Per-body shared-memory struct: [0..5] a = M^-1 J^T x (lin, ang), [6] 1/m, [7..15] I^-1 (row-major).
+// The stride is odd (17 or 7 doubles) so that lanes touching different bodies hit different banks,
+// and every field is at a compile-time offset from one base address (no per-field index math).
+template <bool MS> struct BodyStride { static constexpr int value = MS ? 17 : 7; };
+
 // t = J a for the block: Rc (vel1 - vel0), vel_b = a_lin + a_ang x r_b.
-__device__ __forceinline__ d3 block_Ja(const BlockRec& r, const double* sa, int n) {
+template <int BS>
+__device__ __forceinline__ d3 block_Ja(const BlockRec& r, const double* sb) {
   d3 u = mk3(0, 0, 0);
   if (r.i1 >= 0) {
-    const int b = r.i1;
-    d3 al = mk3(sa[b], sa[n + b], sa[2 * n + b]);
-    d3 aa = mk3(sa[3 * n + b], sa[4 * n + b], sa[5 * n + b]);
+    const double* q = sb + r.i1 * BS;
+    d3 al = mk3(q[0], q[1], q[2]);
+    d3 aa = mk3(q[3], q[4], q[5]);
     u = al + cross3(aa, r.r1);
   }
   if (r.i0 >= 0) {
-    const int b = r.i0;
-    d3 al = mk3(sa[b], sa[n + b], sa[2 * n + b]);
-    d3 aa = mk3(sa[3 * n + b], sa[4 * n + b], sa[5 * n + b]);
+    const double* q = sb + r.i0 * BS;
+    d3 al = mk3(q[0], q[1], q[2]);
+    d3 aa = mk3(q[3], q[4], q[5]);
     u = u - (al + cross3(aa, r.r0));
   }
   return mmulv(r.Rc, u);
 }
 
-// a += M^-1 J^T delta for the block.  minv: [10][n] = 1/m, Iinv (shared or read-only global).
-template <bool LDG>
-__device__ __forceinline__ void block_scatter(const BlockRec& r, d3 delta, double* sa, const double* minv, int n) {
+// a += M^-1 J^T delta for the block.  MS: M^-1 from the body struct, else from the read-only
+// global array st ([10][n] = 1/m, Iinv).
+template <bool MS>
+__device__ __forceinline__ void block_scatter(const BlockRec& r, d3 delta, double* sb, const double* st, int n) {
+  constexpr int BS = BodyStride<MS>::value;
   d3 imp = mtmulv(r.Rc, delta);
   if (r.i1 >= 0) {
     const int b = r.i1;
+    double* q = sb + b * BS;
     double Ii[9];
-    const double mi = LDG ? __ldg(minv + b) : minv[b];
+    const double mi = MS ? q[6] : __ldg(st + b);
 #pragma unroll
-    for (int k = 0; k < 9; k++) Ii[k] = LDG ? __ldg(minv + (1 + k) * n + b) : minv[(1 + k) * n + b];
+    for (int k = 0; k < 9; k++) Ii[k] = MS ? q[7 + k] : __ldg(st + (1 + k) * n + b);
     d3 da = mmulv(Ii, cross3(r.r1, imp));
-    sa[b] += mi * imp.x; sa[n + b] += mi * imp.y; sa[2 * n + b] += mi * imp.z;
-    sa[3 * n + b] += da.x; sa[4 * n + b] += da.y; sa[5 * n + b] += da.z;
+    q[0] += mi * imp.x; q[1] += mi * imp.y; q[2] += mi * imp.z;
+    q[3] += da.x; q[4] += da.y; q[5] += da.z;
   }
   if (r.i0 >= 0) {
     const int b = r.i0;
+    double* q = sb + b * BS;
     double Ii[9];
-    const double mi = LDG ? __ldg(minv + b) : minv[b];
+    const double mi = MS ? q[6] : __ldg(st + b);
 #pragma unroll
-    for (int k = 0; k < 9; k++) Ii[k] = LDG ? __ldg(minv + (1 + k) * n + b) : minv[(1 + k) * n + b];
+    for (int k = 0; k < 9; k++) Ii[k] = MS ? q[7 + k] : __ldg(st + (1 + k) * n + b);
     d3 da = mmulv(Ii, cross3(r.r0, imp));
-    sa[b] -= mi * imp.x; sa[n + b] -= mi * imp.y; sa[2 * n + b] -= mi * imp.z;
-    sa[3 * n + b] -= da.x; sa[4 * n + b] -= da.y; sa[5 * n + b] -= da.z;
+    q[0] -= mi * imp.x; q[1] -= mi * imp.y; q[2] -= mi * imp.z;
+    q[3] -= da.x; q[4] -= da.y; q[5] -= da.z;
+  }
+}
+
+// Zero the accumulators of a world and (MS) load its M^-1 into the body structs.
+template <bool MS>
+__device__ __forceinline__ void init_bodies(double* sb, const double* st, int n, int lane, int nl) {
+  constexpr int BS = BodyStride<MS>::value;
+  for (int i = lane; i < n * BS; i += nl) {
+    const int b = i / BS, f = i - b * BS;
+    sb[i] = (MS && f >= 6 && f < 16) ? st[(f - 6) * n + b] : 0.0;
   }
 }
 
@@ -339,7 +359,8 @@ __device__ __forceinline__ void residual_rows(const BlockRec& r, d3 t, double x0
 }
 
 // v' = v + dt (M^-1 f + a); p += dt (v+v')/2; R <- WtoQ((w+w')/2, dt) R  for body b of a world.
-__device__ __forceinline__ bool integrate_body(double* dyn, const double* st, const double* sa, int n, int b, double dt) {
+template <int BS>
+__device__ __forceinline__ bool integrate_body(double* dyn, const double* st, const double* sb, int n, int b, double dt) {
   const double mi = __ldg(st + b);
   double Ii[9];
 #pragma unroll
@@ -348,8 +369,8 @@ __device__ __forceinline__ bool integrate_body(double* dyn, const double* st, co
   d3 ft = mk3(st[13 * n + b], st[14 * n + b], st[15 * n + b]);
   d3 v = mk3(dyn[12 * n + b], dyn[13 * n + b], dyn[14 * n + b]);
   d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
-  d3 al = mk3(sa[b], sa[n + b], sa[2 * n + b]);
-  d3 aa = mk3(sa[3 * n + b], sa[4 * n + b], sa[5 * n + b]);
+  d3 al = mk3(sb[b * BS], sb[b * BS + 1], sb[b * BS + 2]);
+  d3 aa = mk3(sb[b * BS + 3], sb[b * BS + 4], sb[b * BS + 5]);
   d3 vn = v + dt * (fl * mi + al);
   d3 wn = wv + dt * (mmulv(Ii, ft) + aa);
   d3 vmid = (v + vn) / 2.0, wmid = (wv + wn) / 2.0;
@@ -413,10 +434,9 @@ __global__ void __launch_bounds__(32) egg_pgs_mw_kernel(EggDev d, double dt, int
   constexpr int G = 32 / LPW;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
-  constexpr int APW = MINV_SMEM ? 16 : 6;     // doubles per body kept in shared memory
-  double* sa = reinterpret_cast<double*>(smraw) + (size_t)sub * APW * n;
-  double* sminv = sa + 6 * n;
-  unsigned char* tab = smraw + (size_t)G * APW * n * 8 + (size_t)sub * tabcap;   // stage sizes (<= LPW each)
+  constexpr int BS = BodyStride<MINV_SMEM>::value;   // doubles per body kept in shared memory
+  double* sa = reinterpret_cast<double*>(smraw) + (size_t)sub * BS * n;
+  unsigned char* tab = smraw + (size_t)G * BS * n * 8 + (size_t)sub * tabcap;   // stage sizes (<= LPW each)
   const double cfm = d.prm.cfm, tol = d.prm.tol;
   const int k_max = d.prm.k_max, nj = d.nj;
 
@@ -430,12 +450,9 @@ __global__ void __launch_bounds__(32) egg_pgs_mw_kernel(EggDev d, double dt, int
     const int* gls = d.level_start + (size_t)wc * (d.nrec + 1);
     const double* recs = d.rec + (size_t)wc * d.nrec * EGG_REC;
     double* lam = d.lam + (size_t)wc * d.nrec * 3;
-    for (int i = sl; i < 6 * n; i += LPW) sa[i] = 0.0;
-    if (MINV_SMEM)
-      for (int i = sl; i < 10 * n; i += LPW) sminv[i] = st[i];
+    init_bodies<MINV_SMEM>(sa, st, n, sl, LPW);
     for (int i = sl; i < ns && i < tabcap; i += LPW) tab[i] = (unsigned char)(gls[i + 1] - gls[i]);
     __syncwarp();
-    const double* minv = MINV_SMEM ? sminv : st;
     auto stage_cnt = [&](int s) -> int { return (s < tabcap) ? (int)tab[s] : (__ldg(gls + s + 1) - __ldg(gls + s)); };
 
     int ns_max = ns, nc_max = nc;
@@ -491,16 +508,16 @@ __global__ void __launch_bounds__(32) egg_pgs_mw_kernel(EggDev d, double dt, int
             unpack_rec(v, r);
             if (pass_kind == 0) {
               lp[0] = r.rhs[0]; lp[1] = r.rhs[1]; lp[2] = r.rhs[2];
-              block_scatter<!MINV_SMEM>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, minv, n);
+              block_scatter<MINV_SMEM>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, st, n);
             } else {
               double c0, c1, c2;
               if (flags & 2) { c0 = __ldcg(lp); c1 = __ldcg(lp + 1); c2 = __ldcg(lp + 2); }
               else { c0 = lp[0]; c1 = lp[1]; c2 = lp[2]; }
-              d3 t3 = block_Ja(r, sa, n);
+              d3 t3 = block_Ja<BS>(r, sa);
               if (pass_kind == 1) {
                 d3 dl = gs_rows(r, t3, c0, c1, c2);
                 lp[0] = c0; lp[1] = c1; lp[2] = c2;
-                block_scatter<!MINV_SMEM>(r, dl, sa, minv, n);
+                block_scatter<MINV_SMEM>(r, dl, sa, st, n);
               } else {
                 residual_rows(r, t3, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
               }
@@ -543,7 +560,7 @@ __global__ void __launch_bounds__(32) egg_pgs_mw_kernel(EggDev d, double dt, int
       }
       double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
       bool bad = false;
-      for (int b = sl; b < n; b += LPW) bad |= integrate_body(dyn, st, sa, n, b, dt);
+      for (int b = sl; b < n; b += LPW) bad |= integrate_body<BS>(dyn, st, sa, n, b, dt);
       if (bad) atomicOr(&d.status[w], 16 /*EGG_ST_NONFINITE*/);
     }
     __syncwarp();
@@ -553,13 +570,14 @@ __global__ void __launch_bounds__(32) egg_pgs_mw_kernel(EggDev d, double dt, int
 // Variant "mwpf": as "mw", plus a register double buffer: the next step's record and multipliers
 // are loaded while the current step computes (costs ~100 registers => 9 warps per SM), M^-1 comes
 // through the read-only L1 path.  Fastest measured variant for wide worlds (n = 64).
-template <int LPW>
+template <int LPW, bool MINV_SMEM>
 __global__ void __launch_bounds__(32) egg_pgs_mwpf_kernel(EggDev d, double dt, int tabcap) {
   constexpr int G = 32 / LPW;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
-  double* sa = reinterpret_cast<double*>(smraw) + (size_t)sub * 6 * n;
-  unsigned char* tab = smraw + (size_t)G * 6 * n * 8 + (size_t)sub * tabcap;   // stage sizes (<= LPW each)
+  constexpr int BS = BodyStride<MINV_SMEM>::value;
+  double* sa = reinterpret_cast<double*>(smraw) + (size_t)sub * BS * n;
+  unsigned char* tab = smraw + (size_t)G * BS * n * 8 + (size_t)sub * tabcap;   // stage sizes (<= LPW each)
   const double cfm = d.prm.cfm, tol = d.prm.tol;
   const int k_max = d.prm.k_max, nj = d.nj;
 
@@ -573,7 +591,7 @@ __global__ void __launch_bounds__(32) egg_pgs_mwpf_kernel(EggDev d, double dt, i
     const int* gls = d.level_start + (size_t)wc * (d.nrec + 1);
     const double* recs = d.rec + (size_t)wc * d.nrec * EGG_REC;
     double* lam = d.lam + (size_t)wc * d.nrec * 3;
-    for (int i = sl; i < 6 * n; i += LPW) sa[i] = 0.0;
+    init_bodies<MINV_SMEM>(sa, st, n, sl, LPW);
     for (int i = sl; i < ns && i < tabcap; i += LPW) tab[i] = (unsigned char)(gls[i + 1] - gls[i]);
     __syncwarp();
     auto stage_cnt = [&](int s) -> int { return (s < tabcap) ? (int)tab[s] : (__ldg(gls + s + 1) - __ldg(gls + s)); };
@@ -645,14 +663,14 @@ __global__ void __launch_bounds__(32) egg_pgs_mwpf_kernel(EggDev d, double dt, i
             double* lp = lam + 3 * (size_t)cur_slot;
             if (pass_kind == 0) {
               lp[0] = r.rhs[0]; lp[1] = r.rhs[1]; lp[2] = r.rhs[2];
-              block_scatter<true>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, st, n);
+              block_scatter<MINV_SMEM>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, st, n);
             } else if (pass_kind == 1) {
-              d3 t3 = block_Ja(r, sa, n);
+              d3 t3 = block_Ja<BS>(r, sa);
               d3 dl = gs_rows(r, t3, c0, c1, c2);
               lp[0] = c0; lp[1] = c1; lp[2] = c2;
-              block_scatter<true>(r, dl, sa, st, n);
+              block_scatter<MINV_SMEM>(r, dl, sa, st, n);
             } else {
-              d3 t3 = block_Ja(r, sa, n);
+              d3 t3 = block_Ja<BS>(r, sa);
               residual_rows(r, t3, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
             }
           }
@@ -697,7 +715,7 @@ __global__ void __launch_bounds__(32) egg_pgs_mwpf_kernel(EggDev d, double dt, i
       }
       double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
       bool bad = false;
-      for (int b = sl; b < n; b += LPW) bad |= integrate_body(dyn, st, sa, n, b, dt);
+      for (int b = sl; b < n; b += LPW) bad |= integrate_body<BS>(dyn, st, sa, n, b, dt);
       if (bad) atomicOr(&d.status[w], 16 /*EGG_ST_NONFINITE*/);
     }
     __syncwarp();
@@ -740,8 +758,8 @@ __global__ void __launch_bounds__(32) egg_pgs_tma_kernel(EggDev d, double dt) {
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x;
   double* sa = reinterpret_cast<double*>(smraw);
-  double* sminv = sa + 6 * n;
-  unsigned char* ring = smraw + (((size_t)16 * n * 8 + 127) & ~(size_t)127);
+  constexpr int BS = BodyStride<true>::value;
+  unsigned char* ring = smraw + (((size_t)BS * n * 8 + 127) & ~(size_t)127);
   unsigned long long* mbar = reinterpret_cast<unsigned long long*>(ring + (size_t)TMA_NSTAGE * TMA_SLOT_BYTES);
   int* sls = reinterpret_cast<int*>(mbar + TMA_NSTAGE);
   const double cfm = d.prm.cfm, tol = d.prm.tol;
@@ -757,8 +775,7 @@ __global__ void __launch_bounds__(32) egg_pgs_tma_kernel(EggDev d, double dt) {
 
   for (int w = blockIdx.x; w < d.W; w += gridDim.x) {
     const double* st = d.stat + (size_t)w * EGG_STAT * n;
-    for (int i = lane; i < 10 * n; i += 32) sminv[i] = st[i];
-    for (int i = lane; i < 6 * n; i += 32) sa[i] = 0.0;
+    init_bodies<true>(sa, st, n, lane, 32);
     const int nc = nj + d.c_count[w];
     const int ns = d.n_levels[w];
     const int* gls = d.level_start + (size_t)w * (d.nrec + 1);
@@ -811,14 +828,14 @@ __global__ void __launch_bounds__(32) egg_pgs_tma_kernel(EggDev d, double dt) {
             if (ns == 1 && pass_kind != 0) { c0 = __ldcg(lp); c1 = __ldcg(lp + 1); c2 = __ldcg(lp + 2); }
             if (pass_kind == 0) {
               lp[0] = r.rhs[0]; lp[1] = r.rhs[1]; lp[2] = r.rhs[2];
-              block_scatter<false>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, sminv, n);
+              block_scatter<true>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, st, n);
             } else if (pass_kind == 1) {
-              d3 t = block_Ja(r, sa, n);
+              d3 t = block_Ja<BS>(r, sa);
               d3 dl = gs_rows(r, t, c0, c1, c2);
               lp[0] = c0; lp[1] = c1; lp[2] = c2;
-              block_scatter<false>(r, dl, sa, sminv, n);
+              block_scatter<true>(r, dl, sa, st, n);
             } else {
-              d3 t = block_Ja(r, sa, n);
+              d3 t = block_Ja<BS>(r, sa);
               residual_rows(r, t, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
             }
           }
@@ -858,7 +875,7 @@ __global__ void __launch_bounds__(32) egg_pgs_tma_kernel(EggDev d, double dt) {
     }
     double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
     bool bad = false;
-    for (int b = lane; b < n; b += 32) bad |= integrate_body(dyn, st, sa, n, b, dt);
+    for (int b = lane; b < n; b += 32) bad |= integrate_body<BS>(dyn, st, sa, n, b, dt);
     if (__any_sync(0xffffffffu, bad) && lane == 0) d.status[w] |= 16 /*EGG_ST_NONFINITE*/;
     __syncwarp();
   }
@@ -893,9 +910,9 @@ template <int LPW, bool MINV_SMEM>
 void launch_mw2(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
   int tabcap = d.nrec + 1;
-  if (tabcap > 2048) tabcap = 2048;
+  if (tabcap > 512) tabcap = 512;
   tabcap = (tabcap + 15) & ~15;
-  size_t smem = (size_t)G * (MINV_SMEM ? 16 : 6) * d.n * 8 + (size_t)G * tabcap;
+  size_t smem = (size_t)G * (MINV_SMEM ? 17 : 7) * d.n * 8 + (size_t)G * tabcap;
   cudaFuncSetAttribute(egg_pgs_mw_kernel<LPW, MINV_SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 16);
   int groups = (d.W + G - 1) / G;
@@ -906,14 +923,20 @@ template <int LPW>
 void launch_mwpf(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
   int tabcap = d.nrec + 1;
-  if (tabcap > 2048) tabcap = 2048;
+  if (tabcap > 512) tabcap = 512;
   tabcap = (tabcap + 15) & ~15;
-  size_t smem = (size_t)G * 6 * d.n * 8 + (size_t)G * tabcap;
-  cudaFuncSetAttribute(egg_pgs_mwpf_kernel<LPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool ms = env_int("EGG_PGS_MINV_SMEM", 1) != 0;
+  size_t smem = (size_t)G * (ms ? 17 : 7) * d.n * 8 + (size_t)G * tabcap;
   int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 9);
   int groups = (d.W + G - 1) / G;
   int grid = groups < num_sms() * per_sm ? groups : num_sms() * per_sm;
-  egg_pgs_mwpf_kernel<LPW><<<grid, 32, smem, s>>>(d, dt, tabcap);
+  if (ms) {
+    cudaFuncSetAttribute(egg_pgs_mwpf_kernel<LPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_pgs_mwpf_kernel<LPW, true><<<grid, 32, smem, s>>>(d, dt, tabcap);
+  } else {
+    cudaFuncSetAttribute(egg_pgs_mwpf_kernel<LPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_pgs_mwpf_kernel<LPW, false><<<grid, 32, smem, s>>>(d, dt, tabcap);
+  }
 }
 template <int LPW>
 void launch_mw(const EggDev& d, double dt, cudaStream_t s) {
@@ -949,7 +972,7 @@ void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s) {
 
 void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) {
   if (use_tma_variant()) {
-    size_t smem = (((size_t)16 * d.n * 8 + 127) & ~(size_t)127) + (size_t)TMA_NSTAGE * TMA_SLOT_BYTES + TMA_NSTAGE * 8 + (size_t)(TMA_LS_CAP + 1) * 4;
+    size_t smem = (((size_t)17 * d.n * 8 + 127) & ~(size_t)127) + (size_t)TMA_NSTAGE * TMA_SLOT_BYTES + TMA_NSTAGE * 8 + (size_t)(TMA_LS_CAP + 1) * 4;
     cudaFuncSetAttribute(egg_pgs_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 12);
     int grid = d.W < num_sms() * per_sm ? d.W : num_sms() * per_sm;
