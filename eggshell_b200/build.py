@@ -16,6 +16,7 @@ UNITS = [
     ("egg_collide.cu", ["-fmad=false"]),
     ("egg_solve.cu", []),
     ("egg_pgs.cu", []),
+    ("egg_iter.cu", []),
     ("egg_dense.cu", ["-fmad=false"]),
     ("egg_capi.cu", []),
 ]

@@ -151,8 +151,10 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   }
   DA(d.rec, (size_t)W * d.nrec * EGG_REC);
   DA(d.lam, (size_t)W * d.nrec * 3);
+  DA(d.lam2, (size_t)W * d.nrec * 3);
   DA(d.lam_out, (size_t)W * d.nrec * 3);
   DA(d.row_state, (size_t)W * d.nrec * 3);
+  if (dsc->solver == EGG_SOLVER_JACOBI || dsc->solver == EGG_SOLVER_SOR) DA(d.slot_of, (size_t)W * d.nrec);
   DA(d.level_start, (size_t)W * (d.nrec + 1));
   DA(d.n_levels, W);
   DA(d.status, W);
@@ -337,10 +339,7 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     return EGG_ERR_UNSUPPORTED;
   }
   const int solver = b->dev.prm.solver;
-  if (solver != EGG_SOLVER_PGS && solver != EGG_SOLVER_DENSE_MURTY) {  // Jacobi / SOR: not on the device yet
-    g_err = "solver not implemented on the device yet";
-    return EGG_ERR_UNSUPPORTED;
-  }
+  if (solver < EGG_SOLVER_DENSE_MURTY || solver > EGG_SOLVER_SOR) { g_err = "unknown solver"; return EGG_ERR_ARG; }
   CK(cudaSetDevice(b->device));
   for (int s = 0; s < n_steps; s++) {
     cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -357,7 +356,8 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     egg_launch_assemble(b->dev, dt, b->stream);
     if (b->profiling) CK(cudaEventRecord(e[2], b->stream));
     if (solver == EGG_SOLVER_PGS) egg_launch_solve_pgs(b->dev, dt, b->stream);
-    else egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes);
+    else if (solver == EGG_SOLVER_DENSE_MURTY) egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes);
+    else egg_launch_solve_iter(b->dev, dt, solver, b->stream);
     if (b->profiling) CK(cudaEventRecord(e[3], b->stream));
     b->launches += 3;
   }

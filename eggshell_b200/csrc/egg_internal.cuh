@@ -63,8 +63,10 @@ struct EggDev {
   unsigned char* pair_cnt;
   double* rec;
   double* lam;                // [W][nrec][3] level order during the solve
+  double* lam2;               // second multiplier buffer (fused variant ping-pongs between the two)
   double* lam_out;            // [W][3*nrec] row order (joints then contacts)
   int* row_state;             // [W][3*nrec]
+  int* slot_of;               // [W][nrec] record slot of reference constraint c (Jacobi / SOR only, else null)
   int* level_start;           // [W][nrec+1] start slot of every solver stage (level chunk <= 32 blocks)
   int* n_levels;              // [W] number of stages
   int* status;                // [W]
@@ -115,6 +117,7 @@ void egg_launch_collide(const EggDev& d, cudaStream_t s);
 void egg_launch_init(const EggDev& d, cudaStream_t s);
 void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
 void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
+void egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s);
 void egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s);
 void egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s);
 void egg_launch_unpack(int W, double* aos, int per_world, int comps, const double* soa, int soa_comps, int comp_off, cudaStream_t s);

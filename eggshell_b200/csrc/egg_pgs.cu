@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
     v[REC_IDX] = __hiloint2double(i1, i0);
     v[REC_META] = __hiloint2double(ckind, c);
     v[29] = 0.0;
+    if (d.slot_of) d.slot_of[(size_t)w * d.nrec + c] = slot[c];
     double2* out = reinterpret_cast<double2*>(recw + (size_t)slot[c] * EGG_REC);
 #pragma unroll
     for (int p = 0; p < EGG_PIECES; p++) out[p] = make_double2(v[2 * p], v[2 * p + 1]);
@@ -262,17 +263,17 @@ __device__ __forceinline__ void unpack_rec(const double2* v, BlockRec& r) {
 template <bool MS> struct BodyStride { static constexpr int value = MS ? 17 : 7; };
 
 // t = J a for the block: Rc (vel1 - vel0), vel_b = a_lin + a_ang x r_b.
-template <int BS>
+template <int BS, int OFF = 0>
 __device__ __forceinline__ d3 block_Ja(const BlockRec& r, const double* sb) {
   d3 u = mk3(0, 0, 0);
   if (r.i1 >= 0) {
-    const double* q = sb + r.i1 * BS;
+    const double* q = sb + r.i1 * BS + OFF;
     d3 al = mk3(q[0], q[1], q[2]);
     d3 aa = mk3(q[3], q[4], q[5]);
     u = al + cross3(aa, r.r1);
   }
   if (r.i0 >= 0) {
-    const double* q = sb + r.i0 * BS;
+    const double* q = sb + r.i0 * BS + OFF;
     d3 al = mk3(q[0], q[1], q[2]);
     d3 aa = mk3(q[3], q[4], q[5]);
     u = u - (al + cross3(aa, r.r0));
@@ -282,17 +283,16 @@ __device__ __forceinline__ d3 block_Ja(const BlockRec& r, const double* sb) {
 
 // a += M^-1 J^T delta for the block.  MS: M^-1 from the body struct, else from the read-only
 // global array st ([10][n] = 1/m, Iinv).
-template <bool MS>
+template <bool MS, int BS = BodyStride<MS>::value, int MO = 6>
 __device__ __forceinline__ void block_scatter(const BlockRec& r, d3 delta, double* sb, const double* st, int n) {
-  constexpr int BS = BodyStride<MS>::value;
   d3 imp = mtmulv(r.Rc, delta);
   if (r.i1 >= 0) {
     const int b = r.i1;
     double* q = sb + b * BS;
     double Ii[9];
-    const double mi = MS ? q[6] : __ldg(st + b);
+    const double mi = MS ? q[MO] : __ldg(st + b);
 #pragma unroll
-    for (int k = 0; k < 9; k++) Ii[k] = MS ? q[7 + k] : __ldg(st + (1 + k) * n + b);
+    for (int k = 0; k < 9; k++) Ii[k] = MS ? q[MO + 1 + k] : __ldg(st + (1 + k) * n + b);
     d3 da = mmulv(Ii, cross3(r.r1, imp));
     q[0] += mi * imp.x; q[1] += mi * imp.y; q[2] += mi * imp.z;
     q[3] += da.x; q[4] += da.y; q[5] += da.z;
@@ -301,9 +301,9 @@ __device__ __forceinline__ void block_scatter(const BlockRec& r, d3 delta, doubl
     const int b = r.i0;
     double* q = sb + b * BS;
     double Ii[9];
-    const double mi = MS ? q[6] : __ldg(st + b);
+    const double mi = MS ? q[MO] : __ldg(st + b);
 #pragma unroll
-    for (int k = 0; k < 9; k++) Ii[k] = MS ? q[7 + k] : __ldg(st + (1 + k) * n + b);
+    for (int k = 0; k < 9; k++) Ii[k] = MS ? q[MO + 1 + k] : __ldg(st + (1 + k) * n + b);
     d3 da = mmulv(Ii, cross3(r.r0, imp));
     q[0] -= mi * imp.x; q[1] -= mi * imp.y; q[2] -= mi * imp.z;
     q[3] -= da.x; q[4] -= da.y; q[5] -= da.z;
@@ -311,12 +311,11 @@ __device__ __forceinline__ void block_scatter(const BlockRec& r, d3 delta, doubl
 }
 
 // Zero the accumulators of a world and (MS) load its M^-1 into the body structs.
-template <bool MS>
+template <bool MS, int BS = BodyStride<MS>::value, int MO = 6>
 __device__ __forceinline__ void init_bodies(double* sb, const double* st, int n, int lane, int nl) {
-  constexpr int BS = BodyStride<MS>::value;
   for (int i = lane; i < n * BS; i += nl) {
     const int b = i / BS, f = i - b * BS;
-    sb[i] = (MS && f >= 6 && f < 16) ? st[(f - 6) * n + b] : 0.0;
+    sb[i] = (MS && f >= MO && f < MO + 10) ? st[(f - MO) * n + b] : 0.0;
   }
 }
 
@@ -359,7 +358,7 @@ __device__ __forceinline__ void residual_rows(const BlockRec& r, d3 t, double x0
 }
 
 // v' = v + dt (M^-1 f + a); p += dt (v+v')/2; R <- WtoQ((w+w')/2, dt) R  for body b of a world.
-template <int BS>
+template <int BS, int OFF = 0>
 __device__ __forceinline__ bool integrate_body(double* dyn, const double* st, const double* sb, int n, int b, double dt) {
   const double mi = __ldg(st + b);
   double Ii[9];
@@ -369,8 +368,8 @@ __device__ __forceinline__ bool integrate_body(double* dyn, const double* st, co
   d3 ft = mk3(st[13 * n + b], st[14 * n + b], st[15 * n + b]);
   d3 v = mk3(dyn[12 * n + b], dyn[13 * n + b], dyn[14 * n + b]);
   d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
-  d3 al = mk3(sb[b * BS], sb[b * BS + 1], sb[b * BS + 2]);
-  d3 aa = mk3(sb[b * BS + 3], sb[b * BS + 4], sb[b * BS + 5]);
+  d3 al = mk3(sb[b * BS + OFF], sb[b * BS + OFF + 1], sb[b * BS + OFF + 2]);
+  d3 aa = mk3(sb[b * BS + OFF + 3], sb[b * BS + OFF + 4], sb[b * BS + OFF + 5]);
   d3 vn = v + dt * (fl * mi + al);
   d3 wn = wv + dt * (mmulv(Ii, ft) + aa);
   d3 vmid = (v + vn) / 2.0, wmid = (wv + wn) / 2.0;
@@ -722,6 +721,188 @@ __global__ void __launch_bounds__(32) egg_pgs_mwpf_kernel(EggDev d, double dt, i
   }
 }
 
+// Variant "fused" (default for wide worlds): as "mwpf", but the termination residual of sweep k is
+// evaluated INSIDE sweep k+1 (from a frozen copy a_prev of the accumulator and the multipliers of
+// sweep k), so the records are streamed once per sweep instead of twice and a sweep has one
+// pass of stages instead of two.  Sweep k+1 is therefore speculative: if the residual of sweep k
+// turns out to be <= tol the kernel returns x_k / a_prev and discards x_{k+1} (the multipliers
+// ping-pong between two buffers).  Results, sweep counts and clamp states are identical to the
+// unfused order of operations (sparse_iterations.cc:204-222).
+// Body struct: [0..5] a, [6..11] a_prev, [12..21] 1/m, I^-1 (MS), odd stride.
+template <bool MS> struct FusedStride { static constexpr int value = MS ? 23 : 13; };
+
+template <int LPW, bool MINV_SMEM>
+__global__ void __launch_bounds__(32) egg_pgs_fused_kernel(EggDev d, double dt, int tabcap) {
+  constexpr int G = 32 / LPW;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
+  constexpr int BS = FusedStride<MINV_SMEM>::value;
+  constexpr int MO = 12;
+  double* sa = reinterpret_cast<double*>(smraw) + (size_t)sub * BS * n;
+  unsigned char* tab = smraw + (size_t)G * BS * n * 8 + (size_t)sub * tabcap;
+  const double cfm = d.prm.cfm, tol = d.prm.tol;
+  const int k_max = d.prm.k_max, nj = d.nj;
+
+  for (int wbase = blockIdx.x * G; wbase < d.W; wbase += gridDim.x * G) {
+    const int w = wbase + sub;
+    const bool valid = w < d.W;
+    const int wc = valid ? w : d.W - 1;
+    const double* st = d.stat + (size_t)wc * EGG_STAT * n;
+    const int nc = valid ? nj + d.c_count[wc] : 0;
+    const int ns = valid ? d.n_levels[wc] : 0;
+    const int* gls = d.level_start + (size_t)wc * (d.nrec + 1);
+    const double* recs = d.rec + (size_t)wc * d.nrec * EGG_REC;
+    double* lamb[2] = {d.lam + (size_t)wc * d.nrec * 3, d.lam2 + (size_t)wc * d.nrec * 3};
+    init_bodies<MINV_SMEM, BS, MO>(sa, st, n, sl, LPW);
+    for (int i = sl; i < ns && i < tabcap; i += LPW) tab[i] = (unsigned char)(gls[i + 1] - gls[i]);
+    __syncwarp();
+    auto stage_cnt = [&](int s) -> int { return (s < tabcap) ? (int)tab[s] : (__ldg(gls + s + 1) - __ldg(gls + s)); };
+
+    int ns_max = ns, nc_max = nc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ns_max = max(ns_max, __shfl_xor_sync(0xffffffffu, ns_max, o));
+      nc_max = max(nc_max, __shfl_xor_sync(0xffffffffu, nc_max, o));
+    }
+    const int nchunk = (nc_max + LPW - 1) / LPW;
+
+    bool active = nc > 0, use_prev = false;
+    double err = 0.0;
+    int it = 0;          // accepted sweeps of this world
+    int k = 0;           // accepted sweeps of the still-active worlds (warp-uniform)
+    int rd = 0;          // buffer holding x_k
+    int pass_kind = 0;   // 0: x0 = rhs scatter, 3: fused residual(k) + update(k -> k+1), 2: residual only
+    double2 cur[EGG_PIECES], nxt[EGG_PIECES];
+    double c0 = 0, c1 = 0, c2 = 0, p0 = 0, p1 = 0, p2 = 0;
+    int cur_slot = -1, nxt_slot = -1;
+    int s0_next = 0;
+    auto fetch = [&](int slot, bool with_lam) {
+      nxt_slot = slot;
+      if (slot >= 0) {
+        const double2* rp = reinterpret_cast<const double2*>(recs + (size_t)slot * EGG_REC);
+#pragma unroll
+        for (int p = 0; p < EGG_PIECES; p++) nxt[p] = __ldg(rp + p);
+        if (with_lam) {
+          const double* lq = lamb[rd] + 3 * (size_t)slot;
+          p0 = __ldcg(lq); p1 = __ldcg(lq + 1); p2 = __ldcg(lq + 2);
+        }
+      }
+    };
+    auto stage_slot = [&](int s) -> int {
+      if (!active || s >= ns) return -1;
+      const int cnt = stage_cnt(s);
+      const int mine = (sl < cnt) ? s0_next + sl : -1;
+      s0_next += cnt;
+      return mine;
+    };
+    auto chunk_slot = [&](int c) -> int {
+      const int f = c * LPW + sl;
+      return (active && f < nc) ? f : -1;
+    };
+    auto load_lam_for_next = [&]() {   // multipliers of the prefetched first step of the next pass
+      if (nxt_slot >= 0) {
+        const double* lq = lamb[rd] + 3 * (size_t)nxt_slot;
+        p0 = __ldcg(lq); p1 = __ldcg(lq + 1); p2 = __ldcg(lq + 2);
+      }
+    };
+
+    if (__any_sync(0xffffffffu, active)) {
+      s0_next = 0;
+      fetch(stage_slot(0), false);
+      while (true) {
+        const int nsteps = (pass_kind == 2) ? nchunk : ns_max;
+        double se = 0, s1 = 0, s2 = 0, s3 = 0;
+        if (pass_kind == 3) {   // freeze a_k: the residual of sweep k is taken against it
+          for (int b = sl; active && b < n; b += LPW) {
+            double* q = sa + b * BS;
+#pragma unroll
+            for (int f = 0; f < 6; f++) q[6 + f] = q[f];
+          }
+          __syncwarp();
+        }
+        for (int t = 0; t < nsteps; t++) {
+#pragma unroll
+          for (int p = 0; p < EGG_PIECES; p++) cur[p] = nxt[p];
+          cur_slot = nxt_slot; c0 = p0; c1 = p1; c2 = p2;
+          const bool last = (t + 1 == nsteps);
+          // within a pass the read buffer is never written, so next-step multipliers can be
+          // prefetched; across a pass boundary only the record is (its buffer is chosen later)
+          if (!last) fetch(pass_kind == 2 ? chunk_slot(t + 1) : stage_slot(t + 1), pass_kind != 0);
+          if (cur_slot >= 0) {
+            BlockRec r;
+            unpack_rec(cur, r);
+            if (pass_kind == 0) {
+              double* lp = lamb[0] + 3 * (size_t)cur_slot;
+              lp[0] = r.rhs[0]; lp[1] = r.rhs[1]; lp[2] = r.rhs[2];
+              block_scatter<MINV_SMEM, BS, MO>(r, mk3(r.rhs[0], r.rhs[1], r.rhs[2]), sa, st, n);
+            } else if (pass_kind == 3) {
+              d3 tp = block_Ja<BS, 6>(r, sa);
+              residual_rows(r, tp, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
+              d3 t3 = block_Ja<BS, 0>(r, sa);
+              d3 dl = gs_rows(r, t3, c0, c1, c2);
+              double* lp = lamb[rd ^ 1] + 3 * (size_t)cur_slot;
+              lp[0] = c0; lp[1] = c1; lp[2] = c2;
+              block_scatter<MINV_SMEM, BS, MO>(r, dl, sa, st, n);
+            } else {
+              d3 t3 = block_Ja<BS, 0>(r, sa);
+              residual_rows(r, t3, c0, c1, c2, r.orig < nj, cfm, se, s1, s2, s3);
+            }
+          }
+          __syncwarp();
+        }
+        if (pass_kind == 0) {
+          pass_kind = (k_max > 0) ? 3 : 2;
+        } else {
+#pragma unroll
+          for (int o = LPW / 2; o > 0; o >>= 1) {
+            se += __shfl_xor_sync(0xffffffffu, se, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+          }
+          if (active) {
+            err = sqrt(se) + (sqrt(s1) + sqrt(s2) + sqrt(s3));   // residual of x_k
+            if (pass_kind == 2) {
+              active = false;                                    // k == k_max: x_k is final, a is final
+            } else if (err > tol) {
+              ++it; rd ^= 1;                                     // accept x_{k+1}
+            } else {
+              active = false; use_prev = true;                   // x_k had converged: drop x_{k+1}
+            }
+          }
+          if (!__any_sync(0xffffffffu, active)) break;
+          ++k;
+          pass_kind = (k >= k_max) ? 2 : 3;
+        }
+        // first step of the next pass
+        s0_next = 0;
+        fetch(pass_kind == 2 ? chunk_slot(0) : stage_slot(0), false);
+        load_lam_for_next();
+      }
+    }
+    __syncwarp();
+
+    if (valid) {
+      const double* lamf = lamb[rd];
+      for (int s = sl; s < nc; s += LPW) write_solution(d, w, recs, lamf, s);
+      if (sl == 0) {
+        int* stt = d.stats + (size_t)w * 8;
+        stt[4] = it;
+        stt[5] = 0;
+        stt[6] = (cfm != 0.0);
+        stt[7] = ns;
+        d.resid[w] = err;
+      }
+      double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+      bool bad = false;
+      for (int b = sl; b < n; b += LPW)
+        bad |= use_prev ? integrate_body<BS, 6>(dyn, st, sa, n, b, dt) : integrate_body<BS, 0>(dyn, st, sa, n, b, dt);
+      if (bad) atomicOr(&d.status[w], 16 /*EGG_ST_NONFINITE*/);
+    }
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Variant "tma": one world per warp, a stage's records staged through a shared-memory ring by
 // TMA bulk copies (cp.async.bulk + mbarrier complete_tx).  Kept selectable (EGG_PGS_VARIANT=tma)
@@ -899,12 +1080,15 @@ bool use_tma_variant() {
   const char* e = getenv("EGG_PGS_VARIANT");
   return e && e[0] == 't';
 }
-// Register-prefetch variant: default for wide worlds, EGG_PGS_VARIANT=mw / mwpf overrides.
-bool use_pf_variant(const EggDev& d) {
+// Variant selection: EGG_PGS_VARIANT = mw | mwpf | fused | tma; default fused for wide worlds
+// (n > 24), mw otherwise.
+int pgs_variant(const EggDev& d) {   // 0 mw, 1 mwpf, 2 fused
   const char* e = getenv("EGG_PGS_VARIANT");
-  if (e && e[0] == 'm') return e[1] == 'w' && e[2] == 'p';
-  return d.n > 24;
+  if (e && e[0] == 'f') return 2;
+  if (e && e[0] == 'm') return (e[1] == 'w' && e[2] == 'p') ? 1 : 0;
+  return d.n > 24 ? 2 : 0;
 }
+bool use_pf_variant(const EggDev& d) { return pgs_variant(d) != 0; }
 
 template <int LPW, bool MINV_SMEM>
 void launch_mw2(const EggDev& d, double dt, cudaStream_t s) {
@@ -918,6 +1102,25 @@ void launch_mw2(const EggDev& d, double dt, cudaStream_t s) {
   int groups = (d.W + G - 1) / G;
   int grid = groups < num_sms() * per_sm ? groups : num_sms() * per_sm;
   egg_pgs_mw_kernel<LPW, MINV_SMEM><<<grid, 32, smem, s>>>(d, dt, tabcap, env_int("EGG_PGS_FLAGS", 0));
+}
+template <int LPW>
+void launch_fused(const EggDev& d, double dt, cudaStream_t s) {
+  constexpr int G = 32 / LPW;
+  int tabcap = d.nrec + 1;
+  if (tabcap > 512) tabcap = 512;
+  tabcap = (tabcap + 15) & ~15;
+  const bool ms = env_int("EGG_PGS_MINV_SMEM", 1) != 0;
+  size_t smem = (size_t)G * (ms ? 23 : 13) * d.n * 8 + (size_t)G * tabcap;
+  int per_sm = env_int("EGG_PGS_CTAS_PER_SM", ms ? 6 : 9);
+  int groups = (d.W + G - 1) / G;
+  int grid = groups < num_sms() * per_sm ? groups : num_sms() * per_sm;
+  if (ms) {
+    cudaFuncSetAttribute(egg_pgs_fused_kernel<LPW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_pgs_fused_kernel<LPW, true><<<grid, 32, smem, s>>>(d, dt, tabcap);
+  } else {
+    cudaFuncSetAttribute(egg_pgs_fused_kernel<LPW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_pgs_fused_kernel<LPW, false><<<grid, 32, smem, s>>>(d, dt, tabcap);
+  }
 }
 template <int LPW>
 void launch_mwpf(const EggDev& d, double dt, cudaStream_t s) {
@@ -979,7 +1182,12 @@ void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) {
     egg_pgs_tma_kernel<<<grid, 32, smem, s>>>(d, dt);
     return;
   }
-  if (use_pf_variant(d)) {
+  if (pgs_variant(d) == 2) {
+    if (egg_stage_cap(d) == 4) launch_fused<4>(d, dt, s);
+    else launch_fused<8>(d, dt, s);
+    return;
+  }
+  if (pgs_variant(d) == 1) {
     if (egg_stage_cap(d) == 4) launch_mwpf<4>(d, dt, s);
     else launch_mwpf<8>(d, dt, s);
     return;

@@ -279,3 +279,32 @@ def test_cpp_host_mirror_demo():
     j = lines.index("cairn 4")
     cairn = np.array([[float(x) for x in ln.split()[1:]] for ln in lines[j + 1:j + 5]])
     assert np.all(cairn[:, 5] < 0)      # the rocks are falling
+
+
+# ---------------------------------------------------------------------------------------------
+# The other matrix-free solvers of sparse_iterations.h: Jacobi and backward SOR.
+@pytest.mark.parametrize("solver,name", [(2, "jacobi"), (3, "sor")])
+def test_jacobi_sor_stepwise(solver, name):
+    import eggshell_b200 as E
+    # Jacobi is not a contraction on these systems (the reference only runs it on diagonally
+    # dominant test matrices): a few sweeps keep rounding differences from being amplified.
+    km = 6 if solver == 2 else 25
+    for scene, steps, kw in ((E.scenes.cairn(8, rocks=4, zb=(0.2, 0.5), seed=31), 12, dict(k_max=40 if solver == 3 else km, cfm=0.1)),
+                             (E.scenes.legged20(2, seed=5000), 2, dict(k_max=km, cfm=0.1)),
+                             (E.scenes.stack10(2, seed=1000), 2, dict(k_max=km, cfm=0.1))):
+        idx = list(range(scene["W"]))
+        b = E.scenes.make_batch(scene, solver=solver, taps=True, **kw)
+        ows = [oracle_world(scene, wi, solver=solver, **kw)[0] for wi in idx]
+        for s in range(steps):
+            p, R, v, w = b.bodies()
+            for k, wi in enumerate(idx):
+                ows[k].set_state(p[wi], R[wi], v[wi], w[wi])
+            b.step(scene["dt"])
+            for ow in ows:
+                ow.step(scene["dt"])
+            worst = compare_step(b, ows, idx, tol=1e-8)
+            st = b.status()
+            for k, wi in enumerate(idx):
+                assert st["sweeps"][wi] == ows[k].stats()["sweeps"], (name, scene["name"], s, wi)
+            assert worst["lam"] <= 1e-6, (name, scene["name"], worst)
+        b.close()
