@@ -137,6 +137,7 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   DA(d.dyn, (size_t)W * EGG_DYN * n);
   DA(d.stat, (size_t)W * EGG_STAT * n);
   DA(d.bpar, (size_t)W * EGG_BPAR * n);
+  DA(d.minv_aos, (size_t)W * (n + 1) * 10);
   DA(d.j_i0, (size_t)W * nj);
   DA(d.j_i1, (size_t)W * nj);
   DA(d.jc, (size_t)W * 6 * nj);

@@ -51,6 +51,7 @@ struct EggDev {
   double* dyn;
   double* stat;
   double* bpar;
+  double* minv_aos;           // [W][n+1][10] = 1/m, I^-1 per body (row n = 0: the dummy 'world' body)
   int* j_i0;
   int* j_i1;
   double* jc;
@@ -117,6 +118,7 @@ void egg_launch_collide(const EggDev& d, cudaStream_t s);
 void egg_launch_init(const EggDev& d, cudaStream_t s);
 void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
 void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
+void egg_launch_solve_pgs_fast(const EggDev& d, double dt, int lpw, cudaStream_t s);
 void egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s);
 void egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s);
 void egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s);

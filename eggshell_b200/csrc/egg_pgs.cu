@@ -1080,13 +1080,14 @@ bool use_tma_variant() {
   const char* e = getenv("EGG_PGS_VARIANT");
   return e && e[0] == 't';
 }
-// Variant selection: EGG_PGS_VARIANT = mw | mwpf | fused | tma; default fused for wide worlds
-// (n > 24), mw otherwise.
-int pgs_variant(const EggDev& d) {   // 0 mw, 1 mwpf, 2 fused
+// Variant selection: EGG_PGS_VARIANT = mw | mwpf | fused | fast | tma; default fast
+// (egg_pgs_fast.cu: fused residual, cp.async-staged records).
+int pgs_variant(const EggDev& d) {   // 0 mw, 1 mwpf, 2 fused, 3 fast
   const char* e = getenv("EGG_PGS_VARIANT");
+  if (e && e[0] == 'f' && e[1] == 'a') return 3;
   if (e && e[0] == 'f') return 2;
   if (e && e[0] == 'm') return (e[1] == 'w' && e[2] == 'p') ? 1 : 0;
-  return d.n > 24 ? 2 : 0;
+  return 3;
 }
 bool use_pf_variant(const EggDev& d) { return pgs_variant(d) != 0; }
 
@@ -1157,7 +1158,8 @@ int egg_stage_cap(const EggDev& d) {
   if (use_tma_variant()) return TMA_CAP;
   int lpw = env_int("EGG_PGS_LPW", 0);
   if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16 && lpw != 32) lpw = 8;
-  if (use_pf_variant(d) && lpw != 4) lpw = 8;
+  if (pgs_variant(d) == 3) { if (lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 4 : 8; }
+  else if (use_pf_variant(d) && lpw != 4) lpw = 8;
   return lpw;
 }
 
@@ -1180,6 +1182,10 @@ void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) {
     int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 12);
     int grid = d.W < num_sms() * per_sm ? d.W : num_sms() * per_sm;
     egg_pgs_tma_kernel<<<grid, 32, smem, s>>>(d, dt);
+    return;
+  }
+  if (pgs_variant(d) == 3) {
+    egg_launch_solve_pgs_fast(d, dt, egg_stage_cap(d), s);
     return;
   }
   if (pgs_variant(d) == 2) {

@@ -41,6 +41,11 @@ __global__ void egg_init_kernel(EggDev d) {
   const double m = bp[3 * n + b];
   st[0 * n + b] = 1.0 / m;     // ensembles.cc:207
   for (int k = 0; k < 9; k++) st[(1 + k) * n + b] = inv[k];
+  {
+    double* ma = d.minv_aos + ((size_t)w * (n + 1) + b) * 10;
+    ma[0] = 1.0 / m;
+    for (int k = 0; k < 9; k++) ma[1 + k] = inv[k];
+  }
   d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
   // f_ext = [m g ; ((-[w]x) I_g) w]   ensembles.cc:218-220
   double ncm[9] = {-0.0, wv.z, -wv.y, -wv.z, -0.0, wv.x, wv.y, -wv.x, -0.0};
