@@ -153,6 +153,7 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   DA(d.rec, (size_t)W * d.nrec * EGG_REC);
   DA(d.lam, (size_t)W * d.nrec * 3);
   DA(d.lam2, (size_t)W * d.nrec * 3);
+  if (dsc->solver == EGG_SOLVER_PGS && getenv("EGG_PGS_MINV") && atoi(getenv("EGG_PGS_MINV")) == 2) DA(d.rec_minv, (size_t)W * d.nrec * 20);
   DA(d.lam_out, (size_t)W * d.nrec * 3);
   DA(d.row_state, (size_t)W * d.nrec * 3);
   if (dsc->solver == EGG_SOLVER_JACOBI || dsc->solver == EGG_SOLVER_SOR) DA(d.slot_of, (size_t)W * d.nrec);

@@ -64,6 +64,7 @@ struct EggDev {
   unsigned char* pair_cnt;
   double* rec;
   double* lam;                // [W][nrec][3] level order during the solve
+  double* rec_minv;           // [W][nrec][20] M^-1 of each block's two bodies, slot order (PGS only, may be null)
   double* lam2;               // second multiplier buffer (fused variant ping-pongs between the two)
   double* lam_out;            // [W][3*nrec] row order (joints then contacts)
   int* row_state;             // [W][3*nrec]

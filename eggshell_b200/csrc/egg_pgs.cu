@@ -224,6 +224,13 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
     v[REC_META] = __hiloint2double(ckind, c);
     v[29] = 0.0;
     if (d.slot_of) d.slot_of[(size_t)w * d.nrec + c] = slot[c];
+    if (d.rec_minv) {   // per-block copy of M^-1 of body i0 then i1 (zeros for the world / ground side)
+      double* mv = d.rec_minv + ((size_t)w * d.nrec + slot[c]) * 20;
+      for (int k = 0; k < 10; k++) {
+        mv[k] = (i0 >= 0) ? sst[k * n + i0] : 0.0;
+        mv[10 + k] = (i1 >= 0) ? sst[k * n + i1] : 0.0;
+      }
+    }
     double2* out = reinterpret_cast<double2*>(recw + (size_t)slot[c] * EGG_REC);
 #pragma unroll
     for (int p = 0; p < EGG_PIECES; p++) out[p] = make_double2(v[2 * p], v[2 * p + 1]);

@@ -25,7 +25,9 @@ namespace {
 
 #define kInf CUDART_INF
 
-template <bool MS> struct FS { static constexpr int value = MS ? 22 : 14; };   // body stride (doubles)
+// MV = where M^-1 of a block's two bodies comes from: 0 read-only global (scattered LDG), 1 the
+// shared-memory body struct, 2 a per-block copy staged together with the record (coalesced).
+template <int MV> struct FS { static constexpr int value = (MV == 1) ? 22 : 14; };   // body stride (doubles)
 
 struct V3 { double x, y, z; };
 __device__ __forceinline__ V3 v3(double x, double y, double z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -73,16 +75,19 @@ __device__ __forceinline__ V3 rel_t(const double2* v, const double2& p1a, const 
   return v3(RC0 * ux + RC1 * uy + RC2 * uz, RC3 * ux + RC4 * uy + RC5 * uz, RC6 * ux + RC7 * uy + RC8 * uz);
 }
 
-template <int LPW, bool MS, bool STAGED>
+template <int LPW, int MV, bool STAGED>
 __global__ void __launch_bounds__(32) egg_pgs_fast_kernel(EggDev d, double dt, int tabcap) {
   constexpr int G = 32 / LPW;
-  constexpr int BS = FS<MS>::value;
+  constexpr int BS = FS<MV>::value;
+  constexpr bool MS = (MV == 1);
+  static_assert(MV != 2 || STAGED, "per-block M^-1 needs the staged path");
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
   const int nb = n + 1;                                   // + dummy body (index n) with M^-1 = 0
   double* sb = reinterpret_cast<double*>(smraw) + (size_t)sub * BS * nb;
   // STAGED: one staging buffer of LPW records per world, filled by coalesced cp.async
-  constexpr int STG = STAGED ? LPW * EGG_REC * 8 : 0;
+  constexpr int STG_REC = LPW * EGG_REC * 8;                 // staged records
+  constexpr int STG = STAGED ? STG_REC + (MV == 2 ? LPW * 160 : 0) : 0;   // + per-block M^-1 (20 doubles)
   unsigned char* stage = smraw + (size_t)G * BS * nb * 8 + (size_t)sub * STG;
   unsigned char* tab = smraw + (size_t)G * (BS * nb * 8 + STG) + (size_t)sub * tabcap;
   const double cfm = d.prm.cfm, tol = d.prm.tol;
@@ -169,6 +174,7 @@ __global__ void __launch_bounds__(32) egg_pgs_fast_kernel(EggDev d, double dt, i
   }
 
     // one block update / residual evaluation on record v with multipliers (x0,x1,x2)
+    double2 mvr[MV == 2 ? 10 : 1];   // M^-1 of body i0 (5 pieces) then body i1 (5 pieces), MV == 2
     auto step = [&](const double2* v, double x0, double x1, double x2, int slot) {
       if (slot < 0) return;
       int i0 = __double2loint(IDX), i1 = __double2hiint(IDX);
@@ -230,7 +236,8 @@ __global__ void __launch_bounds__(32) egg_pgs_fast_kernel(EggDev d, double dt, i
       const double ix = RC0 * d0 + RC3 * d1 + RC6 * d2, iy = RC1 * d0 + RC4 * d1 + RC7 * d2, iz = RC2 * d0 + RC5 * d1 + RC8 * d2;
       {
         double m[10];
-        if (MS) { const double2* mq = q1 + 6; _Pragma("unroll") for (int p = 0; p < 5; p++) { double2 tq = mq[p]; m[2 * p] = tq.x; m[2 * p + 1] = tq.y; } }
+        if (MV == 2) { _Pragma("unroll") for (int p = 0; p < 5; p++) { m[2 * p] = mvr[(MV == 2 ? 5 : 0) + (MV == 2 ? p : 0)].x; m[2 * p + 1] = mvr[(MV == 2 ? 5 : 0) + (MV == 2 ? p : 0)].y; } }
+        else if (MS) { const double2* mq = q1 + 6; _Pragma("unroll") for (int p = 0; p < 5; p++) { double2 tq = mq[p]; m[2 * p] = tq.x; m[2 * p + 1] = tq.y; } }
         else { const double2* mq = reinterpret_cast<const double2*>(maos + i1 * 10); _Pragma("unroll") for (int p = 0; p < 5; p++) { double2 tq = __ldg(mq + p); m[2 * p] = tq.x; m[2 * p + 1] = tq.y; } }
         const double cx = R1Y * iz - R1Z * iy, cy = R1Z * ix - R1X * iz, cz = R1X * iy - R1Y * ix;   // r1 x imp
         const double dax = m[1] * cx + m[2] * cy + m[3] * cz, day = m[4] * cx + m[5] * cy + m[6] * cz, daz = m[7] * cx + m[8] * cy + m[9] * cz;
@@ -240,7 +247,8 @@ __global__ void __launch_bounds__(32) egg_pgs_fast_kernel(EggDev d, double dt, i
       }
       {
         double m[10];
-        if (MS) { const double2* mq = q0 + 6; _Pragma("unroll") for (int p = 0; p < 5; p++) { double2 tq = mq[p]; m[2 * p] = tq.x; m[2 * p + 1] = tq.y; } }
+        if (MV == 2) { _Pragma("unroll") for (int p = 0; p < 5; p++) { m[2 * p] = mvr[MV == 2 ? p : 0].x; m[2 * p + 1] = mvr[MV == 2 ? p : 0].y; } }
+        else if (MS) { const double2* mq = q0 + 6; _Pragma("unroll") for (int p = 0; p < 5; p++) { double2 tq = mq[p]; m[2 * p] = tq.x; m[2 * p + 1] = tq.y; } }
         else { const double2* mq = reinterpret_cast<const double2*>(maos + i0 * 10); _Pragma("unroll") for (int p = 0; p < 5; p++) { double2 tq = __ldg(mq + p); m[2 * p] = tq.x; m[2 * p + 1] = tq.y; } }
         const double cx = R0Y * iz - R0Z * iy, cy = R0Z * ix - R0X * iz, cz = R0X * iy - R0Y * ix;   // r0 x imp
         const double dax = m[1] * cx + m[2] * cy + m[3] * cz, day = m[4] * cx + m[5] * cy + m[6] * cz, daz = m[7] * cx + m[8] * cy + m[9] * cz;
@@ -272,6 +280,12 @@ __global__ void __launch_bounds__(32) egg_pgs_fast_kernel(EggDev d, double dt, i
           const unsigned dst = (unsigned)__cvta_generic_to_shared(stage);
           for (unsigned p = sl; p < pieces; p += LPW)
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + p * 16), "l"(src + p * 16) : "memory");
+          if (MV == 2) {
+            const unsigned mpieces = (unsigned)c_cnt * 10;
+            const char* msrc = reinterpret_cast<const char*>(d.rec_minv + ((size_t)wc * d.nrec + c_s0) * 20);
+            for (unsigned p = sl; p < mpieces; p += LPW)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + STG_REC + p * 16), "l"(msrc + p * 16) : "memory");
+          }
           asm volatile("cp.async.commit_group;" ::: "memory");
           if (with_lam && sl < c_cnt) {
             const double* lq = LAMB(rd) + 3 * (unsigned)(c_s0 + sl);
@@ -300,6 +314,11 @@ __global__ void __launch_bounds__(32) egg_pgs_fast_kernel(EggDev d, double dt, i
               const double2* sp = reinterpret_cast<const double2*>(stage) + sl * EGG_PIECES;
 #pragma unroll
               for (int p = 0; p < EGG_PIECES; p++) bufA[p] = sp[p];
+              if (MV == 2) {
+                const double2* mp = reinterpret_cast<const double2*>(stage + STG_REC) + sl * 10;
+#pragma unroll
+                for (int p = 0; p < 10; p++) mvr[MV == 2 ? p : 0] = mp[p];
+              }
             }
             __syncwarp();                          // staging buffer free again
             if (t + 1 < nsteps) { chunk_of(pass_kind, t + 1); issue_copy(wl); }
@@ -469,33 +488,39 @@ int env_i(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int LPW, bool MS, bool STAGED>
+template <int LPW, int MV, bool STAGED>
 void launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
   int tabcap = d.nrec + 1;
-  if (tabcap > 512) tabcap = 512;
+  // stage sizes beyond the cap are read through L1; 128 entries keep six warps of 4 x 64-body
+  // worlds resident (2042 vs 2524 ms per C3 step at 65536 worlds with a 512-entry table)
+  const int tabmax = env_i("EGG_PGS_TABCAP", 128);
+  if (tabcap > tabmax) tabcap = tabmax;
   tabcap = (tabcap + 15) & ~15;
-  size_t smem = (size_t)G * (FS<MS>::value * (d.n + 1) * 8 + (STAGED ? LPW * EGG_REC * 8 : 0)) + (size_t)G * tabcap;
-  cudaFuncSetAttribute(egg_pgs_fast_kernel<LPW, MS, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = (size_t)G * (FS<MV>::value * (d.n + 1) * 8 + (STAGED ? LPW * EGG_REC * 8 + (MV == 2 ? LPW * 160 : 0) : 0)) + (size_t)G * tabcap;
+  cudaFuncSetAttribute(egg_pgs_fast_kernel<LPW, MV, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = env_i("EGG_PGS_CTAS_PER_SM", 12);
   int groups = (d.W + G - 1) / G;
   int grid = groups < sms * per_sm ? groups : sms * per_sm;
-  egg_pgs_fast_kernel<LPW, MS, STAGED><<<grid, 32, smem, s>>>(d, dt, tabcap);
+  egg_pgs_fast_kernel<LPW, MV, STAGED><<<grid, 32, smem, s>>>(d, dt, tabcap);
 }
 
 template <int LPW>
 void launch2(const EggDev& d, double dt, cudaStream_t s) {
-  // M^-1 in shared memory while four warps' worth still fits comfortably; wide worlds (n = 64)
-  // read it through the read-only path instead (measured: 12.0 vs 13.0 ms, C3 8192 worlds K = 20)
+  // M^-1 source (EGG_PGS_MINV: 0 global, 1 shared body struct, 2 staged per block): the body
+  // struct while four warps' worth still fits comfortably, else the per-block copy.
   constexpr int G = 32 / LPW;
-  const size_t with_ms = (size_t)G * (FS<true>::value * (d.n + 1) * 8 + LPW * EGG_REC * 8);
-  const bool ms = env_i("EGG_PGS_MINV_SMEM", with_ms <= 28 * 1024 ? 1 : 0) != 0;
+  const size_t with_ms = (size_t)G * (FS<1>::value * (d.n + 1) * 8 + LPW * EGG_REC * 8);
+  int mv = env_i("EGG_PGS_MINV", with_ms <= 28 * 1024 ? 1 : 0);   // 2 measured no faster than 0 on C3 (12.1 vs 12.2 ms)
   const bool staged = env_i("EGG_PGS_STAGED", 1) != 0;
-  if (ms) { if (staged) launch<LPW, true, true>(d, dt, s); else launch<LPW, true, false>(d, dt, s); }
-  else { if (staged) launch<LPW, false, true>(d, dt, s); else launch<LPW, false, false>(d, dt, s); }
+  if (!d.rec_minv && mv == 2) mv = 0;
+  if (!staged) { if (mv == 1) launch<LPW, 1, false>(d, dt, s); else launch<LPW, 0, false>(d, dt, s); return; }
+  if (mv == 1) launch<LPW, 1, true>(d, dt, s);
+  else if (mv == 2) launch<LPW, 2, true>(d, dt, s);
+  else launch<LPW, 0, true>(d, dt, s);
 }
 
 }  // namespace
