@@ -22,7 +22,7 @@ ST_LCP_FAILED, ST_JOINT_CONFLICT, ST_BAD_INIT, ST_CONTACT_OVERFLOW, ST_NONFINITE
 
 EXPORTS = [
     "egg_desc_default", "egg_create", "egg_destroy", "egg_set_bodies", "egg_set_state", "egg_set_joints",
-    "egg_set_external", "egg_init", "egg_step", "egg_snapshot", "egg_restore", "egg_update_contacts", "egg_get_static", "egg_get_bodies", "egg_get_contacts", "egg_get_pair_hits",
+    "egg_set_external", "egg_init", "egg_init_stabilize", "egg_step", "egg_snapshot", "egg_restore", "egg_update_contacts", "egg_get_static", "egg_get_bodies", "egg_get_contacts", "egg_get_pair_hits",
     "egg_get_status", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
     "egg_launch_count", "egg_capacity", "egg_set_profiling", "egg_get_kernel_ms", "egg_fp64_peak_tflops", "egg_host_alloc", "egg_host_free", "egg_last_error", "egg_version",
 ]
@@ -157,6 +157,13 @@ class Batch:
 
     def init(self):
         _chk(lib().egg_init(self.h), "egg_init")
+
+    def init_stabilize(self, max_steps=100):
+        """Ensemble::InitStabilize; returns (relaxation steps taken [W], final squared error [W])."""
+        steps = np.zeros(self.W, dtype=np.int32)
+        e2 = np.zeros(self.W)
+        _chk(lib().egg_init_stabilize(self.h, int(max_steps), _p(steps), _p(e2)), "egg_init_stabilize")
+        return steps, e2
 
     def set_stream(self, cuda_stream_ptr):
         _chk(lib().egg_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "egg_set_stream")

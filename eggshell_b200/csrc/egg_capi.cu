@@ -13,6 +13,8 @@
 void egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes);
 size_t egg_dense_scratch_bytes(const EggDev& d);
 double egg_measure_fp64_tflops();
+void egg_launch_relax(const EggDev& d, double dt, double step_scale, int max_steps, void* scratch, int* prog, double* err2, int* any_active,
+                      cudaStream_t s);
 
 static thread_local std::string g_err;
 static void set_err(const char* what, cudaError_t e) {
@@ -329,6 +331,52 @@ int egg_init(egg_batch* b) {
   b->launches += (b->dev.nj > 0) ? 2 : 1;
   CK(cudaGetLastError());
   b->initialised = true;
+  return EGG_OK;
+}
+
+int egg_init_stabilize(egg_batch* b, int max_steps, int* steps_out, double* err_sq_out) {
+  if (!b || max_steps < 0) return EGG_ERR_ARG;
+  if (!b->initialised) { g_err = "egg_init_stabilize before egg_init"; return EGG_ERR_STATE; }
+  CK(cudaSetDevice(b->device));
+  const int W = b->dev.W;
+  if (!b->dense_scratch) {
+    b->dense_scratch_bytes = egg_dense_scratch_bytes(b->dev);
+    char* p = nullptr;
+    int r = dalloc(b, &p, b->dense_scratch_bytes);
+    if (r != EGG_OK) return r;
+    b->dense_scratch = p;
+  }
+  int* prog = nullptr;
+  double* err2 = nullptr;
+  int* any = nullptr;
+  { int r = dalloc(b, &prog, (size_t)2 * W); if (r != EGG_OK) return r; }
+  { int r = dalloc(b, &err2, (size_t)W); if (r != EGG_OK) return r; }
+  { int r = dalloc(b, &any, (size_t)1); if (r != EGG_OK) return r; }
+  EggDev nodedup = b->dev;
+  nodedup.prm.min_dist = -1.0;   // UpdateContacts only: the loop of ensembles.cc:610-617 never de-duplicates
+  const double dt = 0.001 * 500;   // kSimTimeStep * 500 (ensembles.cc:611)
+  for (int it = 0; it <= max_steps; it++) {
+    egg_launch_collide(nodedup, b->stream);
+    egg_launch_assemble(nodedup, dt, b->stream);
+    CK(cudaMemsetAsync(any, 0, sizeof(int), b->stream));
+    egg_launch_relax(nodedup, dt, 0.2, max_steps, b->dense_scratch, prog, err2, any, b->stream);
+    b->launches += 3;
+    int h_any = 0;
+    CK(cudaMemcpyAsync(&h_any, any, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    if (!h_any) break;
+  }
+  egg_launch_collide(b->dev, b->stream);   // CheckAndCorrectEnsembleState (ensembles.cc:618)
+  b->launches++;
+  if (steps_out) {
+    std::vector<int> h((size_t)2 * W);
+    CK(cudaMemcpyAsync(h.data(), prog, h.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int w = 0; w < W; w++) steps_out[w] = h[2 * w];
+  }
+  if (err_sq_out) CK(cudaMemcpyAsync(err_sq_out, err2, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaGetLastError());
   return EGG_OK;
 }
 

@@ -516,6 +516,141 @@ __global__ void __launch_bounds__(DT) egg_dense_kernel(EggDev d, double dt, doub
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Position relaxation: one iteration of Ensemble::InitStabilize's loop body
+// (/root/reference/eggshell/ensembles.cc:602-622): StepPositionRelaxation(dt = 0.5) =
+// StepPositions_ExplicitEuler(dt, -0.2 J^T (J J^T)^-1 err)  (:647-650, 659-666, 553-561) for every
+// world whose squared position error still exceeds 1e-9 and whose step counter is below
+// max_steps.  Contacts must have been refreshed WITHOUT de-duplication (the reference only runs
+// CheckAndCorrectEnsembleState after the loop) and the records assembled for the current state.
+// prog[w] = {steps taken, active flag}; err2[w] = squared error seen by this call.
+__global__ void __launch_bounds__(DT) egg_relax_kernel(EggDev d, double dt, double step_scale, int max_steps, double* scratch,
+                                                        size_t per_world, int Rcap, int* prog, double* err2, int* any_active) {
+  const int w = blockIdx.x, tid = threadIdx.x, n = d.n, nj = d.nj;
+  const int nc = nj + d.c_count[w];
+  const int R = 3 * nc;
+  __shared__ double s_e2;
+  __shared__ int s_go;
+  double* base = scratch + (size_t)w * per_world;
+  double* A = base;
+  double* F = A + (size_t)Rcap * Rcap * 2;
+  double* Jb = F + (size_t)Rcap * Rcap + (size_t)Rcap * (Rcap + 1);
+  double* vec = Jb + (size_t)(Rcap / 3 + 1) * 72;
+  double* e = vec;                 // err [R], reference row order
+  double* y = vec + Rcap;
+  double* tmp = vec + 2 * Rcap;
+  int* ivec = reinterpret_cast<int*>(base + per_world) - 4 * Rcap;
+  int* tr = ivec;
+  int* ci0 = ivec + 2 * Rcap;
+  int* ci1 = ivec + 3 * Rcap;
+  const double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+  const double* recs = d.rec + (size_t)w * d.nrec * EGG_REC;
+  const double* geom = d.c_geom + (size_t)w * 7 * d.maxc;
+  const bool fits = R <= Rcap;
+
+  // J blocks + position error per constraint, reference order
+  for (int s = tid; fits && s < nc; s += DT) {
+    const double* r = recs + (size_t)s * EGG_REC;
+    const int i0 = __double2loint(r[REC_IDX]), i1 = __double2hiint(r[REC_IDX]);
+    const int c = __double2loint(r[REC_META]);
+    ci0[c] = i0; ci1[c] = i1;
+    d3 r0 = mk3(r[REC_R0], r[REC_R0 + 1], r[REC_R0 + 2]), r1 = mk3(r[REC_R1], r[REC_R1 + 1], r[REC_R1 + 2]);
+    double* J0 = Jb + (size_t)c * 72;
+    double* J1 = J0 + 18;
+    for (int k = 0; k < 3; k++) {
+      d3 rc = mk3(r[REC_RC + 3 * k], r[REC_RC + 3 * k + 1], r[REC_RC + 3 * k + 2]);
+      d3 a0 = cross3(rc, r0), a1 = cross3(r1, rc);
+      const double z0 = (i0 >= 0) ? 1.0 : 0.0, z1 = (i1 >= 0) ? 1.0 : 0.0;
+      J0[6 * k] = -rc.x * z0; J0[6 * k + 1] = -rc.y * z0; J0[6 * k + 2] = -rc.z * z0; J0[6 * k + 3] = a0.x * z0; J0[6 * k + 4] = a0.y * z0; J0[6 * k + 5] = a0.z * z0;
+      J1[6 * k] = rc.x * z1; J1[6 * k + 1] = rc.y * z1; J1[6 * k + 2] = rc.z * z1; J1[6 * k + 3] = a1.x * z1; J1[6 * k + 4] = a1.y * z1; J1[6 * k + 5] = a1.z * z1;
+    }
+    if (c < nj) {                                            // joints.cc:3-11
+      d3 p0 = mk3(dyn[i0], dyn[n + i0], dyn[2 * n + i0]);
+      d3 er;
+      if (i1 < 0) {
+        const double* jc = d.jc + (size_t)w * 6 * nj;
+        er = p0 + r0 - mk3(jc[3 * nj + c], jc[4 * nj + c], jc[5 * nj + c]);
+      } else {
+        er = p0 + r0 - mk3(dyn[i1], dyn[n + i1], dyn[2 * n + i1]) - r1;
+      }
+      e[3 * c] = er.x; e[3 * c + 1] = er.y; e[3 * c + 2] = er.z;
+    } else {                                                 // contact.cc:14-22
+      e[3 * c] = 0.0; e[3 * c + 1] = 0.0; e[3 * c + 2] = -geom[6 * d.maxc + (c - nj)];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double s2 = 0;
+    for (int i = 0; fits && i < R; i++) s2 += e[i] * e[i];
+    s_e2 = s2;
+    const int steps = prog[2 * w];
+    s_go = (fits && s2 > 1e-9 && steps < max_steps) ? 1 : 0;
+    err2[w] = s2;
+    prog[2 * w + 1] = s_go;
+    if (s_go) { prog[2 * w] = steps + 1; atomicOr(any_active, 1); }
+    if (!fits) atomicOr(&d.status[w], 32 /*EGG_ST_DENSE_OVERFLOW*/);
+  }
+  __syncthreads();
+  if (!s_go) return;
+
+  // A = J J^T (ensembles.cc:664), blocks over shared bodies in ascending body order
+  for (int q = tid; q < nc * nc; q += DT) {
+    const int c = q / nc, c2 = q % nc;
+    const int a0 = ci0[c], a1 = ci1[c], e0 = ci0[c2], e1 = ci1[c2];
+    double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pass = 0; pass < 2; pass++) {
+      const int side = ((a0 <= a1) == (pass == 0)) ? 0 : 1;
+      const int bd = side ? a1 : a0;
+      if (bd < 0) continue;
+      int side2 = -1;
+      if (bd == e0) side2 = 0; else if (bd == e1) side2 = 1;
+      if (side2 < 0) continue;
+      const double* Jx = Jb + (size_t)c * 72 + 18 * side;
+      const double* Jy = Jb + (size_t)c2 * 72 + 18 * side2;
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) {
+          double s2 = blk[3 * k + l];
+          for (int t = 0; t < 6; t++) s2 += Jx[6 * k + t] * Jy[6 * l + t];
+          blk[3 * k + l] = s2;
+        }
+    }
+    for (int k = 0; k < 3; k++)
+      for (int l = 0; l < 3; l++) A[(size_t)(3 * c + k) * R + 3 * c2 + l] = blk[3 * k + l];
+  }
+  for (int i = tid; i < R; i += DT) y[i] = e[i];
+  __syncthreads();
+  ldlt_compute(A, R, R, tr, tmp);
+  ldlt_solve(A, R, R, tr, y);
+
+  // velocity_correction = -step_scale J^T y ; StepPositions_ExplicitEuler(dt, .)
+  double* dynw = d.dyn + (size_t)w * EGG_DYN * n;
+  for (int bd = tid; bd < n; bd += DT) {
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < nc; c++)
+      for (int side = 0; side < 2; side++) {
+        if ((side ? ci1[c] : ci0[c]) != bd) continue;
+        const double* Jx = Jb + (size_t)c * 72 + 18 * side;
+        for (int k = 0; k < 3; k++)
+          for (int t = 0; t < 6; t++) g[t] += (-1.0 * step_scale * Jx[6 * k + t]) * y[3 * c + k];
+      }
+    d3 p = mk3(dynw[bd], dynw[n + bd], dynw[2 * n + bd]) + dt * mk3(g[0], g[1], g[2]);
+    d3 wv = mk3(g[3], g[4], g[5]);
+    double z2 = dot3(wv, wv);
+    d3 axis = (z2 > 0) ? wv / sqrt(z2) : wv;
+    double ha = 0.5 * (norm3(wv) * dt);
+    double qw = cos(ha), sn = sin(ha);
+    double qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
+    double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
+    double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+    double Q[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+    double Rm[9], Rn[9];
+    for (int k = 0; k < 9; k++) Rm[k] = dynw[(3 + k) * n + bd];
+    mmulm(Q, Rm, Rn);
+    dynw[bd] = p.x; dynw[n + bd] = p.y; dynw[2 * n + bd] = p.z;
+    for (int k = 0; k < 9; k++) dynw[(3 + k) * n + bd] = Rn[k];
+  }
+}
+
 }  // namespace
 
 // Rows the dense path is provisioned for: EGG_DENSE_ROWS or min(3 nrec, 336), a multiple of 3.
@@ -541,4 +676,11 @@ void egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* sc
   const size_t pw = per_world_doubles(Rcap);
   size_t smem = (size_t)6 * d.n * sizeof(double);
   egg_dense_kernel<<<d.W, DT, smem, s>>>(d, dt, reinterpret_cast<double*>(scratch), pw, Rcap);
+}
+
+void egg_launch_relax(const EggDev& d, double dt, double step_scale, int max_steps, void* scratch, int* prog, double* err2, int* any_active,
+                      cudaStream_t s) {
+  const int Rcap = egg_dense_row_cap(d);
+  const size_t pw = per_world_doubles(Rcap);
+  egg_relax_kernel<<<d.W, DT, 0, s>>>(d, dt, step_scale, max_steps, reinterpret_cast<double*>(scratch), pw, Rcap, prog, err2, any_active);
 }

@@ -134,16 +134,13 @@ void Ensemble::Step(double dt, Integrator g) {
 }
 
 void Ensemble::InitStabilize() {
-  // ensembles.cc:602-622: relax positions while the squared constraint error exceeds 1e-9.  The
-  // batched relaxation is a "next" row; scenes whose error is already below the
-  // threshold (every built-in scene at t = 0) need no relaxation step.
-  UpdateContacts();
+  // ensembles.cc:602-622 on the device: relax positions while the squared constraint error exceeds
+  // 1e-9 (at most 100 relaxations), then CheckAndCorrectEnsembleState.
+  int steps = 0;
   double e2 = 0;
-  for (const auto& j : joints_) { VectorXd e = j->ComputeError(); for (int k = 0; k < e.size(); k++) e2 += e(k) * e(k); }
-  for (const auto& c : contacts_) e2 += c->geometry().depth * c->geometry().depth;
-  std::printf("Initial err_sq : %g\n", e2);
-  if (e2 > 1e-9) Panic("InitStabilize: position relaxation is not implemented on the device yet (err_sq = %g)", e2);
-  std::printf("Pre-stabilization steps count : 0\nFinal err_sq : %g\n", e2);
+  check(egg_init_stabilize(batch_, 100, &steps, &e2), "egg_init_stabilize");
+  Download(true);
+  std::printf("Pre-stabilization steps count : %d\nFinal err_sq : %g\n", steps, e2);
 }
 
 MatrixXd Ensemble::ComputeJ() const {

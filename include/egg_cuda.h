@@ -105,6 +105,12 @@ int egg_set_external(egg_batch* b, const double* f_ext);
 /* Ensemble::Init (ensembles.cc:24-29): M^-1 blocks, f_ext, initial-condition check. */
 int egg_init(egg_batch* b);
 
+/* Ensemble::InitStabilize (ensembles.cc:602-622): refresh contacts, and while a world's squared
+ * position error exceeds 1e-9 (and fewer than max_steps relaxations were taken, 100 in the
+ * reference) apply StepPositionRelaxation(dt = 0.5, step_scale = 0.2); finally
+ * CheckAndCorrectEnsembleState.  steps_out[W] / err_sq_out[W] may be NULL.  Synchronous. */
+int egg_init_stabilize(egg_batch* b, int max_steps, int* steps_out, double* err_sq_out);
+
 /* n_steps x Ensemble::Step(dt, integrator) (ensembles.cc:390-427) on every world; asynchronous on
  * the batch stream. */
 int egg_step(egg_batch* b, double dt, int integrator, int n_steps);

@@ -706,13 +706,13 @@ inline void step_positions_explicit_euler(World& W, double dt, const Vec& v) {  
     b.R = quat_to_mat(w_to_q(Vec3(v[6 * i + 3], v[6 * i + 4], v[6 * i + 5]), dt)) * b.R;
   }
 }
-inline int init_stabilize(World& W, double* final_err_sq) {   // ensembles.cc:602-622
+inline int init_stabilize(World& W, double* final_err_sq, int max_steps = 100) {   // ensembles.cc:602-622
   update_contacts(W);
   Vec err = position_error(W);
   double e2 = 0;
   for (double x : err) e2 += x * x;
   int steps = 0;
-  while (e2 > kAllowNumericalError && steps < 100) {
+  while (e2 > kAllowNumericalError && steps < max_steps) {
     step_positions_explicit_euler(W, 0.001 * 500, velocity_relaxation(W, 0.2));
     update_contacts(W);
     err = position_error(W);

@@ -269,9 +269,9 @@ class World:
     def init(self):
         return lib().orc_world_init(self.h)
 
-    def init_stabilize(self):
+    def init_stabilize(self, max_steps=100):
         e = C.c_double(0)
-        steps = lib().orc_world_init_stabilize(self.h, C.byref(e))
+        steps = lib().orc_world_init_stabilize_n(self.h, int(max_steps), C.byref(e))
         return steps, e.value
 
     def step(self, dt):

@@ -308,3 +308,60 @@ def test_jacobi_sor_stepwise(solver, name):
                 assert st["sweeps"][wi] == ows[k].stats()["sweeps"], (name, scene["name"], s, wi)
             assert worst["lam"] <= 1e-6, (name, scene["name"], worst)
         b.close()
+
+
+def test_init_stabilize_matches_oracle():
+    """Row f1: Ensemble::InitStabilize (ensembles.cc:602-622) — batched position relaxation, one
+    relaxation at a time from shared state.  Scenes are chosen with a full-rank J J^T (perturbed
+    joint chains; rocks touching the ground with one vertex): with redundant contacts J J^T is
+    singular and -0.2 J^T (J J^T)^-1 err depends on rounding noise in the reference itself."""
+    import eggshell_b200 as E
+    rng = np.random.default_rng(5)
+    chain = E.scenes.chain(6, links=5, anchor=(0.0, 0.0, 3.0))
+    chain["p"] += rng.uniform(-0.02, 0.02, size=chain["p"].shape)       # break the joints by ~2 cm
+    rocks = E.scenes.cairn(16, rocks=2, xb=(-1.0, 1.0), yb=(-1.0, 1.0), zb=(0.235, 0.255), seed=43)
+    total = 0
+    compared_contacts = 0
+    for scene in (chain, rocks):
+        b = E.Batch(scene["W"], scene["n"], scene["nj"], solver=E.SOLVER_PGS)
+        b.set_bodies(scene["p"], scene["R"], scene["v"], scene["w"], scene["m"], scene["I"])
+        if scene["nj"]:
+            b.set_joints(scene["i0"], scene["i1"], scene["c0"], scene["c1"])
+        b.init()                                                         # BAD_INIT is expected for the chain
+        ows = [oracle_world(scene, wi, solver=1)[0] for wi in range(scene["W"])]
+        for it in range(5):
+            p0, R0, v0, w0 = b.bodies()
+            steps, e2 = b.init_stabilize(max_steps=1)
+            p, R, v, w = b.bodies()
+            con = b.contacts()
+            for wi, ow in enumerate(ows):
+                ow.set_state(p0[wi], R0[wi], v0[wi], w0[wi])
+                ow.update_contacts(dedupe=False)
+                rows = ow.rows()
+                nc_ = len(rows["i0"])
+                if nc_:
+                    J = np.zeros((3 * nc_, 6 * scene["n"]))
+                    for k_ in range(nc_):
+                        if rows["i0"][k_] >= 0:
+                            J[3 * k_:3 * k_ + 3, 6 * rows["i0"][k_]:6 * rows["i0"][k_] + 6] = rows["J0"][k_]
+                        if rows["i1"][k_] >= 0:
+                            J[3 * k_:3 * k_ + 3, 6 * rows["i1"][k_]:6 * rows["i1"][k_] + 6] = rows["J1"][k_]
+                    if np.linalg.cond(J @ J.T) > 1e8:
+                        continue                                         # rank-deficient: see docstring
+                    compared_contacts += ow.n_contacts
+                osteps, oe2 = ow.init_stabilize(max_steps=1)
+                assert steps[wi] == osteps, (scene["name"], it, wi, steps[wi], osteps)
+                op, oR, _, _ = ow.bodies()
+                assert rel_err(p[wi], op) <= 1e-8 and rel_err(R[wi], oR) <= 1e-8, (scene["name"], it, wi, rel_err(p[wi], op), rel_err(R[wi], oR))
+                assert con["count"][wi] == ow.n_contacts
+                total += osteps
+        b.close()
+    assert total > 10 and compared_contacts > 0
+    # the full loop terminates: every world ends at err^2 <= 1e-9 or at the 100-step cap
+    b = E.Batch(chain["W"], chain["n"], chain["nj"], solver=E.SOLVER_PGS)
+    b.set_bodies(chain["p"], chain["R"], chain["v"], chain["w"], chain["m"], chain["I"])
+    b.set_joints(chain["i0"], chain["i1"], chain["c0"], chain["c1"])
+    b.init()
+    steps, e2 = b.init_stabilize()
+    assert np.all((e2 <= 1e-9) | (steps == 100)) and np.all(steps > 0)
+    b.close()
