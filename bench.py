@@ -32,7 +32,12 @@ WORKLOADS = {
     "c2": ("stack10", {}, 4096, "4096 worlds x 10-box stack on ground plane, contact-only PGS"),
     "c3": ("pile64", {}, 65536, "65536 worlds x 64-body random box pile, contact-rich PGS"),
     "c5": ("legged20", {}, 131072, "worlds x 20-body legged ensemble (19 ball joints + foot contacts), PGS"),
+    # MPC rollout sweep (BASELINE.json configs[4]): a timed "step" = one 50-step horizon from the
+    # common start state (egg_restore + 50 x egg_step, state evolving inside the horizon) followed
+    # by the cost kernel and the one NCCL allgather; value counts every world-step of the horizon.
+    "c5mpc": ("legged20", {}, 131072, "MPC rollout sweep: worlds x 20-body legged ensemble, 50-step horizons, cost allgather"),
 }
+HORIZON = {"c5mpc": 50}
 FLOPS_PER_ROW_UPDATE = 54.0
 ROW_STREAM_BYTES = 240.0      # one row streamed from HBM
 
@@ -103,12 +108,13 @@ def run_reference(args):
     total = args.steps + args.warmup
     per_step = max(2.0, min(20.0, 120.0 / max(total, 1)))
     # warm-up samples (untimed), then K timed samples
+    hz = HORIZON.get(args.workload, 1)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference(args, cores, 1.0)
+        cpu_reference(args, cores, 1.0, hz)
     vals, sec, ws, rps = [], 0.0, 0, 0.0
     res = None
     for _ in range(args.steps):
-        res = cpu_reference(args, cores, per_step)
+        res = cpu_reference(args, cores, per_step, hz)
         sec += res["seconds"]
         ws += res["world_steps"]
         rps += res["rows_per_s"] * res["seconds"]
@@ -196,7 +202,8 @@ def run_ours(args):
     W = args.worlds or Wd
     scene = scene_for(args, W, rank)
     n, nj, dt = scene["n"], scene["nj"], scene["dt"]
-    maxc = {"c3": 1024, "c2": 0, "c5": 0}[args.workload]
+    maxc = {"c3": 1024}.get(args.workload, 0)
+    horizon = HORIZON.get(args.workload, 1)
     b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=args.k_max, max_contacts=maxc, device=local)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
@@ -214,7 +221,7 @@ def run_ours(args):
     # ---- warm-up ----
     for _ in range(max(args.warmup, 0)):
         b.restore()
-        b.step(dt)
+        b.step(dt, n_steps=horizon)
     b.sync()
     b.set_profiling(True)
     b.kernel_ms()
@@ -229,10 +236,15 @@ def run_ours(args):
     e0.record(stream)
     for _ in range(args.steps):
         b.restore()
-        b.step(dt)
-    b.rollout_costs(costs.data_ptr())
-    if world > 1:
-        dist.all_gather_into_tensor(all_costs, costs)
+        b.step(dt, n_steps=horizon)
+        if horizon > 1:                  # MPC: one cost kernel + one allgather per horizon
+            b.rollout_costs(costs.data_ptr())
+            if world > 1:
+                dist.all_gather_into_tensor(all_costs, costs)
+    if horizon == 1:
+        b.rollout_costs(costs.data_ptr())
+        if world > 1:
+            dist.all_gather_into_tensor(all_costs, costs)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -251,7 +263,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = W * world * args.steps / (ms_max * 1e-3)
+    value = W * world * args.steps * horizon / (ms_max * 1e-3)
 
     # ---- end-to-end: host state in pinned memory -> H2D -> step -> D2H, every step ----
     # inputs = the scene's initial state in pinned host memory; outputs land in a second pinned set
@@ -261,20 +273,20 @@ def run_ours(args):
         dst[...] = src
     h2d = d2h = sum(x.nbytes for x in hin)
     for _ in range(1):
-        b.set_state(*hin); b.step(dt); b.bodies(out=hout)
+        b.set_state(*hin); b.step(dt, n_steps=horizon); b.bodies(out=hout)
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record(stream)
     for _ in range(args.e2e_steps):
         b.set_state(*hin)                # egg_set_state: pinned host -> device (+ SoA pack kernels)
-        b.step(dt)                       # egg_step
+        b.step(dt, n_steps=horizon)      # egg_step (x horizon for the MPC workload)
         b.bodies(out=hout)               # egg_get_bodies: device -> pinned host (syncs)
     f1.record(stream)
     barrier()
     t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = W * world * args.e2e_steps / (float(t2.item()) * 1e-3)
+    e2e_value = W * world * args.e2e_steps * horizon / (float(t2.item()) * 1e-3)
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -301,14 +313,14 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as O
-            cpu = cpu_reference(args, O.hardware_concurrency() or 1, args.cpu_seconds)
+            cpu = cpu_reference(args, O.hardware_concurrency() or 1, args.cpu_seconds, horizon)
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "rows_per_s")}
         line = {
             "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "worlds_per_gpu": W, "bodies": n, "joints": nj,
-                       "solver": "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01, "dt": dt, "parallelism": f"worlds sharded x{world}",
+                       "solver": "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01, "dt": dt, "horizon": horizon, "parallelism": f"worlds sharded x{world}",
                        "step": "every timed step = egg_restore(scene state, D2D) + egg_step: all steps do the same work",
                        "l2": "inputs larger than L2 (state %.0f MB + rows %.0f MB per rank)" % (W * n * 34 * 8 / 1e6, W * nc_mean * 256 / 1e6),
                        "mean_contacts_per_world": contacts_mean, "mean_rows_per_world": rows_last / W,
