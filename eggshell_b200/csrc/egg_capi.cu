@@ -37,6 +37,7 @@ struct egg_batch {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   bool initialised = false;
+  bool iso_known = false;     // dev.iso read back from the device after egg_init
   std::vector<void*> allocs;
   long long bytes = 0;
   long long launches = 0;
@@ -165,6 +166,15 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   DA(d.stats, (size_t)W * 8);
   DA(d.resid, W);
   DA(d.cost0, (size_t)W * 2);
+  DA(d.work_ctr, 4);
+  DA(d.minv_iso, (size_t)W * (n + 1) * 2);
+  DA(d.iso_flag, 1);
+  {
+    // record format 1 (multipliers inside the record) belongs to the default "stream" PGS variant;
+    // EGG_PGS_VARIANT=mw|mwpf|fused|fast|tma selects one of the measured alternatives (format 0)
+    const char* pv = getenv("EGG_PGS_VARIANT");
+    d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS && (!pv || pv[0] == 's')) ? 1 : 0;
+  }
   b->stage_bytes = (size_t)W * n * 9 * sizeof(double);
   size_t jb = (size_t)W * (nj > 0 ? nj : 1) * 3 * sizeof(double);
   if (jb > b->stage_bytes) b->stage_bytes = jb;
@@ -331,6 +341,7 @@ int egg_init(egg_batch* b) {
   b->launches += (b->dev.nj > 0) ? 2 : 1;
   CK(cudaGetLastError());
   b->initialised = true;
+  b->iso_known = false;
   return EGG_OK;
 }
 
@@ -391,6 +402,14 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
   const int solver = b->dev.prm.solver;
   if (solver < EGG_SOLVER_DENSE_MURTY || solver > EGG_SOLVER_SOR) { g_err = "unknown solver"; return EGG_ERR_ARG; }
   CK(cudaSetDevice(b->device));
+  if (!b->iso_known) {   // one 4-byte read-back per egg_init: which M^-1 layout the PGS kernel may use
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, b->dev.iso_flag, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    b->dev.iso = (flag != 0) ? 1 : 0;
+    if (getenv("EGG_PGS_ISO") && atoi(getenv("EGG_PGS_ISO")) == 0) b->dev.iso = 0;
+    b->iso_known = true;
+  }
   for (int s = 0; s < n_steps; s++) {
     cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
     if (b->profiling) {

@@ -75,6 +75,11 @@ struct EggDev {
   int* stats;                 // [W][8]
   double* resid;              // [W]
   double* cost0;              // [W][2]
+  double* minv_iso;           // [W][n+1][2] = 1/m, 1/c per body when every inverse inertia is c^-1 I3 (row n = 0)
+  int* iso_flag;              // [1] device: 1 while every body seen by egg_init was isotropic
+  int iso;                    // host copy of iso_flag, valid after the first step following egg_init
+  int* work_ctr;              // [4] world-group queue of the persistent solve kernel
+  int rec_fmt;                // 0: D diagonal in REC_DDIAG, multipliers in lam[]; 1: multipliers in REC_DDIAG, next-stage count in slot 29 (stream variant)
   EggParams prm;
 };
 
@@ -120,6 +125,7 @@ void egg_launch_init(const EggDev& d, cudaStream_t s);
 void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
 void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
 void egg_launch_solve_pgs_fast(const EggDev& d, double dt, int lpw, cudaStream_t s);
+void egg_launch_solve_pgs_stream(const EggDev& d, double dt, int lpw, cudaStream_t s);
 void egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s);
 void egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s);
 void egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s);

@@ -216,9 +216,9 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
     v[REC_R1] = r1.x; v[REC_R1 + 1] = r1.y; v[REC_R1 + 2] = r1.z;
     v[REC_DOFF] = D[3]; v[REC_DOFF + 1] = D[6]; v[REC_DOFF + 2] = D[7];
     for (int k = 0; k < 3; k++) {
-      v[REC_DDIAG + k] = D[4 * k];
       v[REC_INVA + k] = 1.0 / (D[4 * k] + cfm);
       v[REC_RHS + k] = -erp / dt / dt * get3(err, k) - Ju[k];
+      v[REC_DDIAG + k] = d.rec_fmt ? v[REC_RHS + k] : D[4 * k];   // fmt 1: the multipliers, x0 = rhs
     }
     v[REC_IDX] = __hiloint2double(i1, i0);
     v[REC_META] = __hiloint2double(ckind, c);
@@ -234,6 +234,15 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
     double2* out = reinterpret_cast<double2*>(recw + (size_t)slot[c] * EGG_REC);
 #pragma unroll
     for (int p = 0; p < EGG_PIECES; p++) out[p] = make_double2(v[2 * p], v[2 * p + 1]);
+  }
+  if (d.rec_fmt) {
+    // stream variant: the first record of stage s carries the block count of stage s+1 (cyclic)
+    __syncthreads();
+    const int ns = d.n_levels[w];
+    for (int s = tid; s < ns; s += NT) {
+      const int sn = (s + 1 == ns) ? 0 : s + 1;
+      recw[(size_t)gstage[s] * EGG_REC + 29] = __hiloint2double(0, gstage[sn + 1] - gstage[sn]);
+    }
   }
 }
 
@@ -1089,7 +1098,8 @@ bool use_tma_variant() {
 }
 // Variant selection: EGG_PGS_VARIANT = mw | mwpf | fused | fast | tma; default fast
 // (egg_pgs_fast.cu: fused residual, cp.async-staged records).
-int pgs_variant(const EggDev& d) {   // 0 mw, 1 mwpf, 2 fused, 3 fast
+int pgs_variant(const EggDev& d) {   // 0 mw, 1 mwpf, 2 fused, 3 fast, 4 stream
+  if (d.rec_fmt) return 4;
   const char* e = getenv("EGG_PGS_VARIANT");
   if (e && e[0] == 'f' && e[1] == 'a') return 3;
   if (e && e[0] == 'f') return 2;
@@ -1165,7 +1175,8 @@ int egg_stage_cap(const EggDev& d) {
   if (use_tma_variant()) return TMA_CAP;
   int lpw = env_int("EGG_PGS_LPW", 0);
   if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16 && lpw != 32) lpw = 8;
-  if (pgs_variant(d) == 3) { if (lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 4 : 8; }
+  if (pgs_variant(d) == 4) { if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 2 : (d.n <= 24 ? 4 : 8); }
+  else if (pgs_variant(d) == 3) { if (lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 4 : 8; }
   else if (use_pf_variant(d) && lpw != 4) lpw = 8;
   return lpw;
 }
@@ -1189,6 +1200,10 @@ void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) {
     int per_sm = env_int("EGG_PGS_CTAS_PER_SM", 12);
     int grid = d.W < num_sms() * per_sm ? d.W : num_sms() * per_sm;
     egg_pgs_tma_kernel<<<grid, 32, smem, s>>>(d, dt);
+    return;
+  }
+  if (pgs_variant(d) == 4) {
+    egg_launch_solve_pgs_stream(d, dt, egg_stage_cap(d), s);
     return;
   }
   if (pgs_variant(d) == 3) {

@@ -38,6 +38,26 @@ __global__ void egg_init_kernel(EggDev d) {
   mmulm(R, I, RI);
   mmulm(RI, Rt, Ig);           // I_g = (R I) R^T, body.h:58
   inverse3(Ig, inv);           // ensembles.cc:210
+  // Isotropic bodies (I_b = c I3: every body of the reference's Chain / Cairn scenes): R (c I3) R^T
+  // is c I3 up to rounding, and so is its inverse.  Snap a numerically isotropic inverse (deviation
+  // <= 1e-13 relative) to (1/c) I3 exactly, so that the solver can keep two doubles per body; a
+  // body that is not isotropic clears the batch-wide flag and the general kernels run.
+  // EGG_OPT_EXACT_INERTIA (quirks bit 4) keeps the matrix as computed.
+  {
+    const double sdiag = (inv[0] + inv[4] + inv[8]) / 3.0;
+    double dev = fmax(fmax(fabs(inv[0] - sdiag), fabs(inv[4] - sdiag)), fabs(inv[8] - sdiag));
+    dev = fmax(dev, fmax(fmax(fabs(inv[1]), fabs(inv[2])), fmax(fabs(inv[3]), fabs(inv[5]))));
+    dev = fmax(dev, fmax(fabs(inv[6]), fabs(inv[7])));
+    const bool iso = !(d.prm.quirks & 4) && dev <= 1e-13 * fabs(sdiag);
+    if (iso) {
+      for (int k = 0; k < 9; k++) inv[k] = 0.0;
+      inv[0] = inv[4] = inv[8] = sdiag;
+    } else {
+      atomicAnd(d.iso_flag, 0);
+    }
+    double* mi = d.minv_iso + ((size_t)w * (n + 1) + b) * 2;
+    mi[1] = sdiag;
+  }
   const double m = bp[3 * n + b];
   st[0 * n + b] = 1.0 / m;     // ensembles.cc:207
   for (int k = 0; k < 9; k++) st[(1 + k) * n + b] = inv[k];
@@ -45,6 +65,7 @@ __global__ void egg_init_kernel(EggDev d) {
     double* ma = d.minv_aos + ((size_t)w * (n + 1) + b) * 10;
     ma[0] = 1.0 / m;
     for (int k = 0; k < 9; k++) ma[1 + k] = inv[k];
+    d.minv_iso[((size_t)w * (n + 1) + b) * 2] = 1.0 / m;
   }
   d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
   // f_ext = [m g ; ((-[w]x) I_g) w]   ensembles.cc:218-220
@@ -161,6 +182,7 @@ double egg_measure_fp64_tflops() {
 
 void egg_launch_init(const EggDev& d, cudaStream_t s) {
   long long t = (long long)d.W * d.n;
+  cudaMemsetAsync(d.iso_flag, 0xff, sizeof(int), s);   // all ones; cleared by the first non-isotropic body
   egg_init_kernel<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(d);
   if (d.nj > 0) {
     long long tj = (long long)d.W * d.nj;

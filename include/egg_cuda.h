@@ -47,7 +47,11 @@ enum egg_cfm_mode { EGG_CFM_AUTO = 0, EGG_CFM_ALWAYS = 1, EGG_CFM_NEVER = 2 };
 /* Reference quirks kept behind flags (SURVEY.md §8 q1,q2); EGG_QUIRKS_REFERENCE = both on. */
 enum egg_quirk {
   EGG_QUIRK_GS_BOUNDS_SHIFT = 1,      /* sparse_iterations_utils.cc:169,180,229-235 */
-  EGG_QUIRK_DENSE_IGNORES_BOUNDS = 2  /* lcp.cc:298 -> :141-147 */
+  EGG_QUIRK_DENSE_IGNORES_BOUNDS = 2, /* lcp.cc:298 -> :141-147 */
+  /* Not a reference quirk: keep (R I_b R^T)^-1 exactly as computed (ensembles.cc:210).  By default
+   * egg_init snaps a numerically isotropic inverse inertia (|dev| <= 1e-13 relative; every body of
+   * the reference's own scenes) to c^-1 I3, which lets the PGS kernel keep 2 doubles per body. */
+  EGG_OPT_EXACT_INERTIA = 4
 };
 #define EGG_QUIRKS_REFERENCE 3
 
