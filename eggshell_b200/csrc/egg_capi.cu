@@ -338,7 +338,7 @@ int egg_init(egg_batch* b) {
   if (!b) return EGG_ERR_ARG;
   CK(cudaSetDevice(b->device));
   egg_launch_init(b->dev, b->stream);
-  b->launches += (b->dev.nj > 0) ? 2 : 1;
+  b->launches += (b->dev.nj > 0) ? 3 : 2;
   CK(cudaGetLastError());
   b->initialised = true;
   b->iso_known = false;
@@ -406,8 +406,8 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, b->dev.iso_flag, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    b->dev.iso = (flag != 0) ? 1 : 0;
-    if (getenv("EGG_PGS_ISO") && atoi(getenv("EGG_PGS_ISO")) == 0) b->dev.iso = 0;
+    b->dev.iso = !(flag & 1) ? 0 : ((flag & 2) ? 2 : 1);   // 0 general, 1 isotropic, 2 isotropic and uniform
+    if (getenv("EGG_PGS_ISO") && atoi(getenv("EGG_PGS_ISO")) < b->dev.iso) b->dev.iso = atoi(getenv("EGG_PGS_ISO"));
     b->iso_known = true;
   }
   for (int s = 0; s < n_steps; s++) {

@@ -50,10 +50,27 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 __device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar)
+// records stream through L2 once per sweep: evict-first, so that the small per-body arrays stay
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar), "l"(pol)
                : "memory");
+}
+__device__ __forceinline__ unsigned long long policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned long long policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ double2 ldg_keep(const double2* p, unsigned long long pol) {   // read-only, L2 evict-last
+  double2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
+  return r;
 }
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
@@ -100,19 +117,24 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 #define MET v[14].x
 
 enum { MODE_INIT = 0, MODE_UPDATE = 1, MODE_RESID = 2 };
+constexpr int PF_SPAN = 11;   // log2 bytes of an L2 prefetch span (0 = off)
 enum { PH_INIT = 0, PH_PROBE = 1, PH_EXACT = 2, PH_UPDATE = 3 };
 
-// ISO: every body's M^-1 is (1/m) I3, (1/c) I3 exactly (egg_init snaps numerically isotropic
-// inverse inertias, see egg_solve.cu) and comes as one 16-byte load per body.
-template <int LPW, int MINB, bool ISO>
-__global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt) {
+// ISO >= 1: every body's M^-1 is (1/m) I3, (1/c) I3 exactly (egg_init snaps numerically isotropic
+// inverse inertias, see egg_solve.cu) and comes as one 16-byte load per body.  ISO == 2: all
+// bodies of the batch share the same (1/m, 1/c) (every body of the reference is the same cube,
+// body.h:91) and the pair is a kernel constant.
+template <int LPW, int MINB, int ISO>
+__global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt, int pf_span, int dbg) {
   constexpr int G = 32 / LPW;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
-  // shared memory: [mbarrier 16 B][G x n x 6 doubles accumulators][G x LPW x 240 B staging]
+  // shared memory: [mbarrier 16 B][dummy body 48 B: the ground / world anchor, always zero]
+  //                [G x n x 6 doubles accumulators][G x LPW x 240 B staging]
   const unsigned bar = s32(smraw);
-  double* sb = reinterpret_cast<double*>(smraw + 16) + (size_t)sub * 6 * n;
-  unsigned char* stage = smraw + 16 + (size_t)G * 48 * n + (size_t)sub * LPW * RECB;
+  double* sb = reinterpret_cast<double*>(smraw + 64) + (size_t)sub * 6 * n;
+  const int dummy = -(sub * n) - 1;            // body index of the dummy relative to this world's sb
+  unsigned char* stage = smraw + 64 + (size_t)G * 48 * n + (size_t)sub * LPW * RECB;
   const unsigned stage_s = s32(stage);
   const double cfm = d.prm.cfm;
   const int nj = d.nj;
@@ -122,6 +144,11 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
     mbar_init(bar, G);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (lane < 6) reinterpret_cast<double*>(smraw + 16)[lane] = 0.0;
+  const unsigned long long pol = policy_evict_first();
+  const unsigned long long pol_keep = policy_evict_last();
+  double um = 0.0, uc = 0.0;                   // ISO == 2: the batch-wide (1/m, 1/c)
+  if (ISO == 2) { um = d.minv_iso[0]; uc = d.minv_iso[1]; }
   __syncwarp();
   unsigned parity = 0;
   const int ngroups = (d.W + G - 1) / G;
@@ -167,7 +194,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         if (cnt > 0) {
           const unsigned bytes = (unsigned)cnt * RECB;
           mbar_arrive_tx(bar, bytes);
-          bulk_g2s(stage_s, recs + (size_t)s0 * RECB, bytes, bar);
+          bulk_g2s(stage_s, recs + (size_t)((dbg & 2) ? 0 : s0) * RECB, bytes, bar, pol);
         } else {
           mbar_arrive(bar);
         }
@@ -180,21 +207,22 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
       if (slot < 0) return;
       const int i0 = __double2loint(IDX), i1 = __double2hiint(IDX);
       const int j0 = (i0 < 0) ? n : i0, j1 = (i1 < 0) ? n : i1;
-      double2* q1 = reinterpret_cast<double2*>(sb + (i1 < 0 ? 0 : i1) * 6);
-      double2* q0 = reinterpret_cast<double2*>(sb + (i0 < 0 ? 0 : i0) * 6);
-      const double2 z2 = make_double2(0.0, 0.0);
-      // accumulator pieces: (l.x,l.y) (l.z,a.x) (a.y,a.z); the ground / world side reads zeros
-      double2 a1a = z2, a1b = z2, a1c = z2, a0a = z2, a0b = z2, a0c = z2;
-      if (i1 >= 0) { a1a = q1[0]; a1b = q1[1]; a1c = q1[2]; }
-      if (i0 >= 0) { a0a = q0[0]; a0b = q0[1]; a0c = q0[2]; }
+      // accumulator pieces: (l.x,l.y) (l.z,a.x) (a.y,a.z); the ground / world side reads the
+      // all-zero dummy body (never written: its stores are predicated off below)
+      double2* q1 = reinterpret_cast<double2*>(sb + (i1 < 0 ? dummy : i1) * 6);
+      double2* q0 = reinterpret_cast<double2*>(sb + (i0 < 0 ? dummy : i0) * 6);
+      double2 a1a = q1[0], a1b = q1[1], a1c = q1[2];
+      double2 a0a = q0[0], a0b = q0[1], a0c = q0[2];
       constexpr int MN = ISO ? 2 : 10;
       double m1[MN], m0[MN];
-      if (mode != MODE_RESID) {                 // M^-1 of both bodies: issued early, used in the scatter
+      if (ISO == 2) {
+        m1[0] = m0[0] = um; m1[1] = m0[1] = uc;
+      } else if (mode != MODE_RESID) {          // M^-1 of both bodies: issued early, used in the scatter
         const double2* mq1 = reinterpret_cast<const double2*>(maos + j1 * MN);
         const double2* mq0 = reinterpret_cast<const double2*>(maos + j0 * MN);
 #pragma unroll
         for (int p = 0; p < MN / 2; p++) {
-          const double2 t1 = __ldg(mq1 + p), t0 = __ldg(mq0 + p);
+          const double2 t1 = ldg_keep(mq1 + p, pol_keep), t0 = ldg_keep(mq0 + p, pol_keep);
           m1[2 * p] = t1.x; m1[2 * p + 1] = t1.y; m0[2 * p] = t0.x; m0[2 * p + 1] = t0.y;
         }
       }
@@ -239,27 +267,27 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         n2 = fmax(n2, lo2);
         d2 = n2 - x2;
         double* lp = reinterpret_cast<double*>(recs + (size_t)slot * RECB) + REC_DDIAG;
-        lp[0] = n0; lp[1] = n1; lp[2] = n2;
+        if (!(dbg & 1)) { lp[0] = n0; lp[1] = n1; lp[2] = n2; }
       }
       // impulse scatter: a += M^-1 J^T delta
       const double ix = RC0 * d0 + RC3 * d1 + RC6 * d2, iy = RC1 * d0 + RC4 * d1 + RC7 * d2, iz = RC2 * d0 + RC5 * d1 + RC8 * d2;
-      if (i1 >= 0) {
+      {
         const double cx = R1Y * iz - R1Z * iy, cy = R1Z * ix - R1X * iz, cz = R1X * iy - R1Y * ix;   // r1 x imp
         double dax, day, daz;
         if (ISO) { dax = m1[1] * cx; day = m1[1] * cy; daz = m1[1] * cz; }
         else { dax = m1[1] * cx + m1[2] * cy + m1[3] * cz; day = m1[4] * cx + m1[5] * cy + m1[6] * cz; daz = m1[7] * cx + m1[8] * cy + m1[9] * cz; }
         a1a.x += m1[0] * ix; a1a.y += m1[0] * iy; a1b.x += m1[0] * iz;
         a1b.y += dax; a1c.x += day; a1c.y += daz;
-        q1[0] = a1a; q1[1] = a1b; q1[2] = a1c;
+        if (i1 >= 0) { q1[0] = a1a; q1[1] = a1b; q1[2] = a1c; }
       }
-      if (i0 >= 0) {
+      {
         const double cx = R0Y * iz - R0Z * iy, cy = R0Z * ix - R0X * iz, cz = R0X * iy - R0Y * ix;   // r0 x imp
         double dax, day, daz;
         if (ISO) { dax = m0[1] * cx; day = m0[1] * cy; daz = m0[1] * cz; }
         else { dax = m0[1] * cx + m0[2] * cy + m0[3] * cz; day = m0[4] * cx + m0[5] * cy + m0[6] * cz; daz = m0[7] * cx + m0[8] * cy + m0[9] * cz; }
         a0a.x -= m0[0] * ix; a0a.y -= m0[0] * iy; a0b.x -= m0[0] * iz;
         a0b.y -= dax; a0c.x -= day; a0c.y -= daz;
-        q0[0] = a0a; q0[1] = a0b; q0[2] = a0c;
+        if (i0 >= 0) { q0[0] = a0a; q0[1] = a0b; q0[2] = a0c; }
       }
     };
     auto reduce4 = [&]() {
@@ -307,6 +335,25 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           if (t + 1 < nsteps) {
             if (staged) issue(s0 + cnt, (on && t + 1 < ns) ? nxt : 0);
             else { const int b0 = (t + 1) * LPW; issue(b0, on ? max(0, min(LPW, nc - b0)) : 0); }
+          }
+          if (cnt > 0 && phase != PH_PROBE && pf_span > 0) {
+            // HBM -> L2 prefetch in spans of 2^pf_span bytes.  Random ~1 KB reads reach only about
+            // half of the HBM bandwidth (tools/micro/dram_chunk_bench: 3.4 TB/s at 960 B, 5.4 at
+            // 3840 B, 7.0 at 7680 B), so DRAM is asked for whole spans: when the consumer enters
+            // span i the lanes of the world prefetch span i+2 (cyclically: the next sweep streams
+            // the same records again); the 1 KB stage copies then hit L2.
+            const int sp_now = ((s0 + cnt) * RECB - 1) >> pf_span;
+            const int sp_prev = (s0 * RECB - 1) >> pf_span;          // -1 >> k = -1: the first chunk enters span 0
+            if (sp_now != sp_prev) {
+              const int nspan = ((nc * RECB - 1) >> pf_span) + 1;
+              int tgt = sp_now + 2;
+              if (tgt >= nspan) tgt -= nspan;
+              if (tgt >= nspan) tgt = nspan - 1;
+              const int lines = 1 << (pf_span - 7);
+              const char* base = recs + ((size_t)tgt << pf_span);
+              const int lim = nc * RECB - (tgt << pf_span);          // bytes left in the world's records
+              for (int q = sl; q < lines && q * 128 < lim; q += LPW) prefetch_l2(base + q * 128);
+            }
           }
           step(buf, mode, slot, s0);
           __syncwarp();                            // accumulator writes visible to the next stage
@@ -446,10 +493,10 @@ int env_i(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int LPW, int MINB, bool ISO>
+template <int LPW, int MINB, int ISO>
 void launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
-  const size_t smem = 16 + (size_t)G * (48 * d.n + LPW * RECB);
+  const size_t smem = 64 + (size_t)G * (48 * d.n + LPW * RECB);
   cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -462,29 +509,25 @@ void launch(const EggDev& d, double dt, cudaStream_t s) {
   const int groups = (d.W + G - 1) / G;
   const int grid = groups < sms * per_sm ? groups : sms * per_sm;
   cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
-  egg_pgs_stream_kernel<LPW, MINB, ISO><<<grid, 32, smem, s>>>(d, dt);
+  egg_pgs_stream_kernel<LPW, MINB, ISO><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF_SPAN", PF_SPAN), env_i("EGG_PGS_DBG", 0));
 }
-
-}  // namespace
 
 // LPW = lanes per world = maximum blocks per stage the assembly emitted.  Registers are allocated
 // per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler = 168 registers.
-void egg_launch_solve_pgs_stream(const EggDev& d, double dt, int lpw, cudaStream_t s) {
-  if (d.iso) {
-    switch (lpw) {
-      case 1: launch<1, 12, true>(d, dt, s); break;
-      case 2: launch<2, 12, true>(d, dt, s); break;
-      case 4: launch<4, 12, true>(d, dt, s); break;
-      case 16: launch<16, 12, true>(d, dt, s); break;
-      default: launch<8, 12, true>(d, dt, s); break;
-    }
-  } else {
-    switch (lpw) {
-      case 1: launch<1, 8, false>(d, dt, s); break;
-      case 2: launch<2, 8, false>(d, dt, s); break;
-      case 4: launch<4, 8, false>(d, dt, s); break;
-      case 16: launch<16, 8, false>(d, dt, s); break;
-      default: launch<8, 8, false>(d, dt, s); break;
-    }
+template <int MINB, int ISO>
+void launch_lpw(const EggDev& d, double dt, int lpw, cudaStream_t s) {
+  switch (lpw) {
+    case 1: launch<1, MINB, ISO>(d, dt, s); break;
+    case 2: launch<2, MINB, ISO>(d, dt, s); break;
+    case 4: launch<4, MINB, ISO>(d, dt, s); break;
+    case 16: launch<16, MINB, ISO>(d, dt, s); break;
+    default: launch<8, MINB, ISO>(d, dt, s); break;
   }
+}
+}  // namespace
+
+void egg_launch_solve_pgs_stream(const EggDev& d, double dt, int lpw, cudaStream_t s) {
+  if (d.iso == 2) launch_lpw<12, 2>(d, dt, lpw, s);
+  else if (d.iso == 1) launch_lpw<12, 1>(d, dt, lpw, s);
+  else launch_lpw<8, 0>(d, dt, lpw, s);
 }

@@ -38,25 +38,25 @@ __global__ void egg_init_kernel(EggDev d) {
   mmulm(R, I, RI);
   mmulm(RI, Rt, Ig);           // I_g = (R I) R^T, body.h:58
   inverse3(Ig, inv);           // ensembles.cc:210
-  // Isotropic bodies (I_b = c I3: every body of the reference's Chain / Cairn scenes): R (c I3) R^T
-  // is c I3 up to rounding, and so is its inverse.  Snap a numerically isotropic inverse (deviation
-  // <= 1e-13 relative) to (1/c) I3 exactly, so that the solver can keep two doubles per body; a
-  // body that is not isotropic clears the batch-wide flag and the general kernels run.
-  // EGG_OPT_EXACT_INERTIA (quirks bit 4) keeps the matrix as computed.
+  // Isotropic bodies (I_b = c I3 exactly: every body of the reference's Chain / Cairn scenes):
+  // R (c I3) R^T is c I3 up to rounding, and so is its inverse.  When the computed inverse agrees
+  // with (1/c) I3 to 1e-13 relative it is replaced by exactly that, so that the solver can keep
+  // two doubles per body; a body that is not isotropic clears the batch-wide flag (bit 0) and the
+  // general kernels run.  EGG_OPT_EXACT_INERTIA (quirks bit 4) keeps the matrix as computed.
   {
-    const double sdiag = (inv[0] + inv[4] + inv[8]) / 3.0;
-    double dev = fmax(fmax(fabs(inv[0] - sdiag), fabs(inv[4] - sdiag)), fabs(inv[8] - sdiag));
+    const bool diag = I[1] == 0.0 && I[2] == 0.0 && I[3] == 0.0 && I[5] == 0.0 && I[6] == 0.0 && I[7] == 0.0 && I[0] == I[4] && I[0] == I[8];
+    const double ic = 1.0 / I[0];
+    double dev = fmax(fmax(fabs(inv[0] - ic), fabs(inv[4] - ic)), fabs(inv[8] - ic));
     dev = fmax(dev, fmax(fmax(fabs(inv[1]), fabs(inv[2])), fmax(fabs(inv[3]), fabs(inv[5]))));
     dev = fmax(dev, fmax(fabs(inv[6]), fabs(inv[7])));
-    const bool iso = !(d.prm.quirks & 4) && dev <= 1e-13 * fabs(sdiag);
+    const bool iso = !(d.prm.quirks & 4) && diag && dev <= 1e-13 * fabs(ic);
     if (iso) {
       for (int k = 0; k < 9; k++) inv[k] = 0.0;
-      inv[0] = inv[4] = inv[8] = sdiag;
+      inv[0] = inv[4] = inv[8] = ic;
     } else {
       atomicAnd(d.iso_flag, 0);
     }
-    double* mi = d.minv_iso + ((size_t)w * (n + 1) + b) * 2;
-    mi[1] = sdiag;
+    d.minv_iso[((size_t)w * (n + 1) + b) * 2 + 1] = ic;
   }
   const double m = bp[3 * n + b];
   st[0 * n + b] = 1.0 / m;     // ensembles.cc:207
@@ -85,6 +85,16 @@ __global__ void egg_init_kernel(EggDev d) {
     d.resid[w] = 0;
     d.c_count[w] = 0;
   }
+}
+
+// Bit 1 of the isotropy flag: every body of the batch has the same (1/m, 1/c) as body 0 of world 0.
+__global__ void egg_iso_uniform_kernel(EggDev d) {
+  const int n = d.n;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)d.W * n) return;
+  const int w = (int)(gid / n), b = (int)(gid % n);
+  const double* mi = d.minv_iso + ((size_t)w * (n + 1) + b) * 2;
+  if (mi[0] != d.minv_iso[0] || mi[1] != d.minv_iso[1]) atomicAnd(d.iso_flag, ~2);
 }
 
 // CheckInitialConditions (ensembles.cc:224-232): every joint error component within 1e-9.
@@ -182,8 +192,9 @@ double egg_measure_fp64_tflops() {
 
 void egg_launch_init(const EggDev& d, cudaStream_t s) {
   long long t = (long long)d.W * d.n;
-  cudaMemsetAsync(d.iso_flag, 0xff, sizeof(int), s);   // all ones; cleared by the first non-isotropic body
+  cudaMemsetAsync(d.iso_flag, 0xff, sizeof(int), s);   // all ones; bit 0 cleared by a non-isotropic body, bit 1 by a non-uniform one
   egg_init_kernel<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(d);
+  egg_iso_uniform_kernel<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(d);
   if (d.nj > 0) {
     long long tj = (long long)d.W * d.nj;
     egg_init_check_kernel<<<(unsigned)((tj + 127) / 128), 128, 0, s>>>(d);

@@ -16,7 +16,12 @@ scene = fn(W)
 
 
 def run(variant):
-    os.environ["EGG_PGS_VARIANT"] = variant
+    # "stream:1" = variant stream with EGG_PGS_ISO=1 (cap on the isotropic fast-path level)
+    name, _, iso = variant.partition(":")
+    os.environ["EGG_PGS_VARIANT"] = name
+    os.environ.pop("EGG_PGS_ISO", None)
+    if iso:
+        os.environ["EGG_PGS_ISO"] = iso
     b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, taps=True, max_contacts=1024 if wl == "c3" else 0)
     out = []
     for s in range(steps):
