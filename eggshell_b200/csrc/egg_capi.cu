@@ -153,7 +153,24 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
     DA(d.pair_code, (size_t)W * d.P);
     DA(d.pair_cnt, (size_t)W * d.P);
   }
-  DA(d.rec, (size_t)W * d.nrec * EGG_REC);
+  {
+    // record format 1 (multipliers inside the record) belongs to the default "stream" PGS variant;
+    // EGG_PGS_VARIANT=mw|mwpf|fused|fast|tma selects one of the measured alternatives (format 0)
+    const char* pv = getenv("EGG_PGS_VARIANT");
+    d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS && (!pv || pv[0] == 's')) ? 1 : 0;
+  }
+  if (d.rec_fmt) {
+    // group stream of the default PGS variant: G = 32 / lpw worlds share one interleaved record stream
+    d.lpw = egg_stage_cap(d);
+    const int groups = (W + 32 / d.lpw - 1) / (32 / d.lpw);
+    DA(d.rec, egg_stream_rec_bytes(W, d.nrec, d.lpw) / sizeof(double));
+    DA(d.c_pos, (size_t)W * d.nrec);
+    DA(d.st_cnt, (size_t)W * d.nrec);
+    DA(d.round_off, (size_t)groups * (d.nrec + 1));
+    DA(d.grp_info, (size_t)groups * 4);
+  } else {
+    DA(d.rec, (size_t)W * d.nrec * EGG_REC);
+  }
   DA(d.lam, (size_t)W * d.nrec * 3);
   DA(d.lam2, (size_t)W * d.nrec * 3);
   if (dsc->solver == EGG_SOLVER_PGS && getenv("EGG_PGS_MINV") && atoi(getenv("EGG_PGS_MINV")) == 2) DA(d.rec_minv, (size_t)W * d.nrec * 20);
@@ -169,12 +186,6 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   DA(d.work_ctr, 4);
   DA(d.minv_iso, (size_t)W * (n + 1) * 2);
   DA(d.iso_flag, 1);
-  {
-    // record format 1 (multipliers inside the record) belongs to the default "stream" PGS variant;
-    // EGG_PGS_VARIANT=mw|mwpf|fused|fast|tma selects one of the measured alternatives (format 0)
-    const char* pv = getenv("EGG_PGS_VARIANT");
-    d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS && (!pv || pv[0] == 's')) ? 1 : 0;
-  }
   b->stage_bytes = (size_t)W * n * 9 * sizeof(double);
   size_t jb = (size_t)W * (nj > 0 ? nj : 1) * 3 * sizeof(double);
   if (jb > b->stage_bytes) b->stage_bytes = jb;
@@ -365,6 +376,7 @@ int egg_init_stabilize(egg_batch* b, int max_steps, int* steps_out, double* err_
   { int r = dalloc(b, &any, (size_t)1); if (r != EGG_OK) return r; }
   EggDev nodedup = b->dev;
   nodedup.prm.min_dist = -1.0;   // UpdateContacts only: the loop of ensembles.cc:610-617 never de-duplicates
+  nodedup.rec_fmt = 0;           // the relaxation kernel reads per-world records (the group stream is the PGS solver's)
   const double dt = 0.001 * 500;   // kSimTimeStep * 500 (ensembles.cc:611)
   for (int it = 0; it <= max_steps; it++) {
     egg_launch_collide(nodedup, b->stream);

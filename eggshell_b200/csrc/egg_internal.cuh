@@ -78,6 +78,12 @@ struct EggDev {
   double* minv_iso;           // [W][n+1][2] = 1/m, 1/c per body when every inverse inertia is c^-1 I3 (row n = 0)
   int* iso_flag;              // [1] device: 1 while every body seen by egg_init was isotropic
   int iso;                    // host copy of iso_flag, valid after the first step following egg_init
+  // group-stream assembly of the default PGS variant (egg_pgs_stream.cu)
+  int lpw;                    // lanes per world = stage cap; G = 32 / lpw worlds share a warp and a record stream
+  int* c_pos;                 // [W][nrec] stage << 8 | index inside the stage, per constraint
+  unsigned char* st_cnt;      // [W][nrec] blocks per stage
+  unsigned* round_off;        // [groups][nrec+1] byte offset of every round inside the group stream
+  int* grp_info;              // [groups][4] rounds, blocks in round 0, stream bytes
   int* work_ctr;              // [4] world-group queue of the persistent solve kernel
   int rec_fmt;                // 0: D diagonal in REC_DDIAG, multipliers in lam[]; 1: multipliers in REC_DDIAG, next-stage count in slot 29 (stream variant)
   EggParams prm;
@@ -125,7 +131,10 @@ void egg_launch_init(const EggDev& d, cudaStream_t s);
 void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
 void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
 void egg_launch_solve_pgs_fast(const EggDev& d, double dt, int lpw, cudaStream_t s);
-void egg_launch_solve_pgs_stream(const EggDev& d, double dt, int lpw, cudaStream_t s);
+void egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s);
+void egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s);
+size_t egg_stream_rec_bytes(int W, int nrec, int lpw);
+int egg_stage_cap(const EggDev& d);
 void egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s);
 void egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s);
 void egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s);

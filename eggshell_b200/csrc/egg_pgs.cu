@@ -1044,14 +1044,19 @@ void launch_mw(const EggDev& d, double dt, cudaStream_t s) {
 int egg_stage_cap(const EggDev& d) {
   if (use_tma_variant()) return TMA_CAP;
   int lpw = env_int("EGG_PGS_LPW", 0);
+  if (pgs_variant(d) == 4) {
+    // narrow worlds expose little parallelism per level: fewer lanes, more worlds per warp
+    if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 2 : (d.n <= 24 ? 4 : 8);
+    return lpw;
+  }
   if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16 && lpw != 32) lpw = 8;
-  if (pgs_variant(d) == 4) { if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 2 : (d.n <= 24 ? 4 : 8); }
-  else if (pgs_variant(d) == 3) { if (lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 4 : 8; }
+  if (pgs_variant(d) == 3) { if (lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 4 : 8; }
   else if (use_pf_variant(d) && lpw != 4) lpw = 8;
   return lpw;
 }
 
 void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s) {
+  if (d.rec_fmt) { egg_launch_assemble_stream(d, dt, s); return; }
   size_t smem = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double) + (size_t)(7 * d.nrec + d.n + 8) * sizeof(int);
   const int cap = egg_stage_cap(d);
   if (d.nrec <= 128) {
@@ -1073,7 +1078,7 @@ void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) {
     return;
   }
   if (pgs_variant(d) == 4) {
-    egg_launch_solve_pgs_stream(d, dt, egg_stage_cap(d), s);
+    egg_launch_solve_pgs_stream(d, dt, s);
     return;
   }
   if (pgs_variant(d) == 3) {

@@ -1,44 +1,57 @@
-// Variant "stream" of the projected Gauss-Seidel solve (default).
+// Variant "stream" of the projected Gauss-Seidel solve (default) and its group-stream assembly.
 //
-// What the profiles of the "fast" variant said (profiles/r1d_pgs_fast_staged_summary.txt): the
-// solve is latency-bound (FP64 pipe 13 %, issue 21 %, 1.5 warps per scheduler) and the number of
-// worlds in flight per SM is capped by shared memory: 112 B per body (accumulator + the frozen
-// copy the fused residual needs) + a 1920-byte staging buffer + a stage table, and by 227
-// registers per thread.  This variant attacks exactly those:
+// What the profiles said, step by step (profiles/r1d..r1f):
+//   * "fast" variant: latency-bound, worlds in flight per SM capped by shared memory (112 B per
+//     body: accumulator + the frozen copy the fused residual needs) and 227 registers.
+//   * first "stream" version (48 B per body, 11 resident warps): 1.8x faster, but throughput no
+//     longer moved with occupancy (6..11 warps/SM: same time) nor with the M^-1 variant: the record
+//     stream was bound by DRAM *efficiency*.  tools/micro/dram_chunk_bench: random contiguous reads
+//     of 960 B reach 3.4 TB/s on this part, 3840 B 5.4 TB/s, 7680 B 7.0 TB/s; a stage of one
+//     world is ~1 KB.
+// Hence this layout: the G = 32/LPW worlds that share a warp are interleaved in memory round by
+// round ("group stream"), so that ONE bulk copy of ~4 KB feeds a whole warp-stage.
 //
+//   group stream = for round t = 0..R-1:  [48-byte header][records of world 0 in stage t]...[world G-1]
+//   header: u8 start[s] (record index of world s inside the round, start[G] = total), byte 40 =
+//   total of the next round (cyclic), so the size of the next copy is known one round ahead.
+//
+// Algorithm (unchanged in exact arithmetic, reference row order inside every world):
 //   * No frozen accumulator.  The reference evaluates the residual of x_k after every sweep only to
 //     decide "stop / continue" (sparse_iterations.cc:196-215).  The residual is a sum of norms of
 //     non-negative per-row terms (sparse_iterations.cc:51-69), so the same formula over ANY subset
-//     of blocks is a lower bound.  Before each sweep one chunk of <= LPW blocks (the "probe") is
-//     evaluated against a = a_k (nothing has been updated yet, so no copy is needed); if that
-//     partial residual already exceeds 2 tol the decision "continue" is certain and the sweep
-//     runs without any residual work.  Otherwise the full residual is evaluated exactly (one
-//     read-only pass) and the reference's decision is taken on it; the probe then moves to the
-//     chunk that contributed most.  Sweep counts, final multipliers and the reported residual
-//     are those of the reference algorithm; 48 B per body instead of 112.
-//   * The multipliers live inside the record (the slot that used to hold the D diagonal: the row
-//     update is written in increment form  x' = x + (rhs - J a - cfm x) / (D + cfm),  so only
-//     1/(D+cfm) is needed), are staged with it and written back in place.
-//   * A stage's records (cnt x 240 B, contiguous) are staged by ONE cp.async.bulk per world
-//     (TMA bulk copy, mbarrier complete_tx) instead of a ~40-instruction cp.async loop; the
-//     count of the next stage rides in the spare slot of the stage's first record, so no stage
-//     table is kept in shared memory.
-//   * World groups are handed out by an atomic counter (worlds differ 2x in work).
+//     of blocks is a lower bound.  Before each sweep one chunk of <= LPW blocks per world (the
+//     "probe") is evaluated against a = a_k (nothing has been updated yet, so no copy is needed);
+//     if that partial residual already exceeds 2 tol the decision "continue" is certain and the
+//     sweep runs without any residual work.  Otherwise the full residual is evaluated exactly
+//     (one read-only pass) and the reference's decision is taken on it; the probe then moves to
+//     the chunk that contributed most.  Sweep counts, final multipliers and the reported
+//     residual are those of the reference algorithm.
+//   * The multipliers live inside the record (REC_DDIAG slot; the row update is written in
+//     increment form  x' = x + (rhs - J a - cfm x) / (D + cfm),  so only 1/(D+cfm) is needed),
+//     are staged with it and written back in place; the read-only pass that ends a world's solve
+//     also writes them out in reference row order (lam_out / row_state taps).
+//   * World groups are handed out by an atomic counter.
 //
-// Per world: n x 48 B accumulator + LPW x 240 B staging.  64-body worlds: 4992 B -> 11 resident
-// warps of 4 worlds per SM (was 6).
+// Per warp: 64 B + G x n x 48 B accumulators + 96 B + G x LPW x 240 B staging.  64-body worlds:
+// 20128 B -> 11 resident warps of 4 worlds per SM at 168 registers.
 //
 // Replaces: sparse::GaussSeidelIteration + GetResidualError + the velocity/position update, i.e.
 // /root/reference/eggshell/sparse_iterations.cc:148-226,51-69,
-// sparse_iterations_utils.cc:12-21,159-243,495-695, ensembles.cc:535,572-591.
+// sparse_iterations_utils.cc:12-21,159-243,495-695, ensembles.cc:535,572-591; the assembly kernels
+// replace Ensemble::ComputeJ / rhs (ensembles.cc:38-87,156-171,563-570) via egg_record.cuh.
 #include "egg_internal.cuh"
+#include "egg_record.cuh"
 #include <math_constants.h>
 #include <cstdlib>
 
 namespace {
 
 #define kInf CUDART_INF
-constexpr int RECB = EGG_REC * 8;   // 240
+constexpr int SREC = 26;            // doubles per stream record (see the layout below)
+constexpr int RECB = SREC * 8;      // 208 = 13 x 16 B: conflict-free 128-bit shared-memory reads at this stride
+constexpr int SPIECES = SREC / 2;   // 16-byte pieces
+constexpr int LAMB = 32;            // bytes of one block's multipliers (3 doubles + pad = one sector)
+constexpr int BLKB = RECB + LAMB;   // stream bytes per block
 
 __device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
@@ -62,6 +75,9 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
   return p;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned long long policy_evict_last() {
   unsigned long long p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -84,8 +100,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       : "memory");
 }
 
-// record pieces (double2 v[15]) -> fields; layout REC_* of egg_internal.cuh with the multipliers
-// in the REC_DDIAG slot and the next stage's block count in the low word of slot 29
+// Stream record (26 doubles): [0..8] Rc, [9..11] r0, [12..14] r1, [15..17] D off-diagonal,
+// [18..20] 1/(D+cfm), [21..23] rhs, [24] packed (i0+1 | (i1+1) << 10 | kind << 20 | original
+// constraint index << 21), [25] spare.  The multipliers are NOT in the record: a round keeps them
+// in one contiguous array of 32-byte sectors in front of its records, so that the write-back of
+// a warp-stage is a run of consecutive full sectors.  (With the multipliers inside each record
+// the scattered 32-byte stores alone cost 40 % of the stream: tools/micro/stream_bench measures
+// 4.1 TB/s with them against 6.2 read-only and 5.6 with the compact array; and partial-sector
+// stores additionally made L2 fetch every sector it merged: +8 GB reads per launch, profiles/r1f.)
+// As double2 pieces v[13]:
 #define RC0 v[0].x
 #define RC1 v[0].y
 #define RC2 v[1].x
@@ -104,20 +127,185 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 #define DO0 v[7].y
 #define DO1 v[8].x
 #define DO2 v[8].y
-#define LM0 v[9].x
-#define LM1 v[9].y
-#define LM2 v[10].x
-#define IA0 v[10].y
-#define IA1 v[11].x
-#define IA2 v[11].y
-#define RH0 v[12].x
-#define RH1 v[12].y
-#define RH2 v[13].x
-#define IDX v[13].y
-#define MET v[14].x
+#define IA0 v[9].x
+#define IA1 v[9].y
+#define IA2 v[10].x
+#define RH0 v[10].y
+#define RH1 v[11].x
+#define RH2 v[11].y
+#define PKD v[12].x
+
+__device__ __forceinline__ void st_sector(double* p, double a, double b, double c, double e) {   // one aligned 32-byte store
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(e) : "memory");
+}
+
+
+constexpr int HDRB = 64;      // round header bytes (keeps the multiplier sectors 32-byte aligned)
+// bytes of a round with `total` blocks: header, multipliers, records, padded to a sector
+__host__ __device__ inline unsigned round_bytes(int total) { return (unsigned)(HDRB + BLKB * total + 31) & ~31u; }
+constexpr int HDR_NEXT = 40;  // byte: total blocks of the next round (cyclic)
+
+__host__ __device__ inline size_t group_stride_bytes(int nrec, int G) { return ((size_t)nrec * ((size_t)BLKB * G + HDRB + 32) + 255) & ~(size_t)255; }
+
+// ---------------------------------------------------------------------------------------------
+// Assembly 1/3: dependency levels and stages of one world (one warp per world, lane 0 scans).
+//   level(c) = 1 + max level of earlier constraints sharing a body  (constraints in reference
+//   order: joints, then contacts, ensembles.cc:234-239); a level is cut into stages of <= cap.
+// Out: c_pos[c] = stage << 8 | index inside the stage, st_cnt[stage], n_levels = #stages.
+__global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, int wpc) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * wpc + wl;
+  const int n = d.n, nj = d.nj, nrec = d.nrec;
+  // per world: blast[n] | lev[nrec] | pos[nrec] | lcnt[nrec+1] | lstage[nrec+1]   (all u16)
+  const size_t per = (size_t)(n + 4 * nrec + 2 + 7) & ~(size_t)7;
+  unsigned short* blast = reinterpret_cast<unsigned short*>(sm_raw) + (size_t)wl * per;
+  unsigned short* lev = blast + n;
+  unsigned short* pos = lev + nrec;
+  unsigned short* lcnt = pos + nrec;
+  unsigned short* lstage = lcnt + nrec + 1;
+  if (wl >= wpc || w >= d.W) return;
+  const int nc = nj + d.c_count[w];
+  const int* c_i0 = d.c_i0 + (size_t)w * d.maxc;
+  const int* c_i1 = d.c_i1 + (size_t)w * d.maxc;
+  for (int b = lane; b < n; b += 32) blast[b] = 0;          // level + 1 of the last constraint on the body (0 = none)
+  for (int c = lane; c <= nc; c += 32) lcnt[c] = 0;
+  __syncwarp();
+  int nl = 0;
+  if (lane == 0) {
+    for (int c = 0; c < nc; c++) {
+      int i0, i1;
+      if (c < nj) { i0 = d.j_i0[(size_t)w * nj + c]; i1 = d.j_i1[(size_t)w * nj + c]; }
+      else { i0 = __ldg(c_i0 + c - nj); i1 = __ldg(c_i1 + c - nj); }
+      int l = 0;
+      if (i0 >= 0) l = blast[i0];
+      if (i1 >= 0) l = max(l, (int)blast[i1]);
+      if (i0 >= 0) blast[i0] = (unsigned short)(l + 1);
+      if (i1 >= 0) blast[i1] = (unsigned short)(l + 1);
+      lev[c] = (unsigned short)l;
+      pos[c] = lcnt[l]++;
+      nl = max(nl, l + 1);
+    }
+    int ns = 0;
+    unsigned char* sc = d.st_cnt + (size_t)w * nrec;
+    for (int l = 0; l < nl; l++) {
+      const int cnt = lcnt[l];
+      lstage[l] = (unsigned short)ns;
+      for (int k = 0; k < cnt; k += cap) sc[ns++] = (unsigned char)min(cap, cnt - k);
+    }
+    d.n_levels[w] = ns;
+  }
+  __syncwarp();
+  int* cp = d.c_pos + (size_t)w * nrec;
+  for (int c = lane; c < nc; c += 32) {
+    const int p = pos[c];
+    cp[c] = ((lstage[lev[c]] + p / cap) << 8) | (p % cap);
+  }
+}
+
+// Assembly 2/3: round offsets and headers of one group (one warp per group).
+__global__ void __launch_bounds__(128) egg_rounds_kernel(EggDev d, int G) {
+  const int g = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int ngroups = (d.W + G - 1) / G;
+  if (g >= ngroups) return;
+  const int nrec = d.nrec;
+  int R = 0;
+  for (int s = 0; s < G; s++) { const int w = g * G + s; if (w < d.W) R = max(R, d.n_levels[w]); }
+  unsigned char* gs = reinterpret_cast<unsigned char*>(d.rec) + (size_t)g * group_stride_bytes(nrec, G);
+  unsigned* roff = d.round_off + (size_t)g * (nrec + 1);
+  auto total_of = [&](int t) -> int {
+    int tot = 0;
+    for (int s = 0; s < G; s++) { const int w = g * G + s; if (w < d.W && t < d.n_levels[w]) tot += d.st_cnt[(size_t)w * nrec + t]; }
+    return tot;
+  };
+  unsigned base = 0;
+  for (int t0 = 0; t0 < R; t0 += 32) {
+    const int t = t0 + lane;
+    unsigned char hdr[HDRB];
+#pragma unroll
+    for (int k = 0; k < HDRB; k++) hdr[k] = 0;
+    int tot = 0;
+    if (t < R) {
+      for (int s = 0; s < G; s++) {
+        const int w = g * G + s;
+        hdr[s] = (unsigned char)tot;
+        if (w < d.W && t < d.n_levels[w]) tot += d.st_cnt[(size_t)w * nrec + t];
+      }
+      hdr[G] = (unsigned char)tot;
+      hdr[HDR_NEXT] = (unsigned char)total_of(t + 1 == R ? 0 : t + 1);
+    }
+    const unsigned bytes = (t < R) ? round_bytes(tot) : 0u;
+    unsigned incl = bytes;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const unsigned off = base + incl - bytes;
+    if (t < R) {
+      roff[t] = off;
+      uint4* hp = reinterpret_cast<uint4*>(gs + off);
+      const uint4* hs = reinterpret_cast<const uint4*>(hdr);
+#pragma unroll
+      for (int q = 0; q < HDRB / 16; q++) hp[q] = hs[q];
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) {
+    int* gi = d.grp_info + (size_t)g * 4;
+    gi[0] = R;
+    gi[1] = (R > 0) ? total_of(0) : 0;
+    gi[2] = (int)base;
+    gi[3] = 0;
+  }
+}
+
+// Assembly 3/3: one CTA per world builds the records and writes them at their round positions.
+template <int NT>
+__global__ void __launch_bounds__(NT) egg_records_kernel(EggDev d, double dt, int G) {
+  extern __shared__ double sm[];
+  const int n = d.n, nj = d.nj, w = blockIdx.x, tid = threadIdx.x, nrec = d.nrec;
+  double* sdyn = sm;                         // [18][n]
+  double* sst = sm + EGG_DYN * n;            // [16][n]
+  const double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+  const double* st = d.stat + (size_t)w * EGG_STAT * n;
+  for (int i = tid; i < EGG_DYN * n; i += NT) sdyn[i] = dyn[i];
+  for (int i = tid; i < EGG_STAT * n; i += NT) sst[i] = st[i];
+  __syncthreads();
+  const int nc = nj + d.c_count[w];
+  const int g = w / G, sub = w % G;
+  const int* c_i0 = d.c_i0 + (size_t)w * d.maxc;
+  const int* c_i1 = d.c_i1 + (size_t)w * d.maxc;
+  const double* geom = d.c_geom + (size_t)w * 7 * d.maxc;
+  const int* cp = d.c_pos + (size_t)w * nrec;
+  const unsigned* roff = d.round_off + (size_t)g * (nrec + 1);
+  unsigned char* gs = reinterpret_cast<unsigned char*>(d.rec) + (size_t)g * group_stride_bytes(nrec, G);
+  for (int c = tid; c < nc; c += NT) {
+    int i0, i1;
+    if (c < nj) { i0 = d.j_i0[(size_t)w * nj + c]; i1 = d.j_i1[(size_t)w * nj + c]; }
+    else { i0 = c_i0[c - nj]; i1 = c_i1[c - nj]; }
+    double v[EGG_REC];
+    egg_build_record(d, w, c, i0, i1, sdyn, sst, geom, dt, true, v);
+    const int p = cp[c], stg = p >> 8, idx = p & 255;
+    const unsigned ro = roff[stg];
+    const unsigned start = gs[ro + sub];
+    double o[SREC];
+#pragma unroll
+    for (int q = 0; q < 18; q++) o[q] = v[q];                       // Rc, r0, r1, D off-diagonal
+#pragma unroll
+    for (int q = 0; q < 3; q++) { o[18 + q] = v[REC_INVA + q]; o[21 + q] = v[REC_RHS + q]; }
+    const int kind = __double2hiint(v[REC_META]);
+    const unsigned long long pk = (unsigned long long)(i0 + 1) | ((unsigned long long)(i1 + 1) << 10) | ((unsigned long long)kind << 20) | ((unsigned long long)c << 21);
+    o[24] = __longlong_as_double((long long)pk);
+    o[25] = 0.0;
+    const unsigned total = gs[ro + G];
+    double2* lam = reinterpret_cast<double2*>(gs + ro + HDRB + (size_t)LAMB * (start + idx));
+    lam[0] = make_double2(v[REC_RHS], v[REC_RHS + 1]);              // x0 = rhs
+    lam[1] = make_double2(v[REC_RHS + 2], 0.0);
+    double2* out = reinterpret_cast<double2*>(gs + ro + HDRB + (size_t)LAMB * total + (size_t)RECB * (start + idx));
+#pragma unroll
+    for (int q = 0; q < SPIECES; q++) out[q] = make_double2(o[2 * q], o[2 * q + 1]);
+  }
+}
 
 enum { MODE_INIT = 0, MODE_UPDATE = 1, MODE_RESID = 2 };
-constexpr int PF_SPAN = 11;   // log2 bytes of an L2 prefetch span (0 = off)
 enum { PH_INIT = 0, PH_PROBE = 1, PH_EXACT = 2, PH_UPDATE = 3 };
 
 // ISO >= 1: every body's M^-1 is (1/m) I3, (1/c) I3 exactly (egg_init snaps numerically isotropic
@@ -125,32 +313,33 @@ enum { PH_INIT = 0, PH_PROBE = 1, PH_EXACT = 2, PH_UPDATE = 3 };
 // bodies of the batch share the same (1/m, 1/c) (every body of the reference is the same cube,
 // body.h:91) and the pair is a kernel constant.
 template <int LPW, int MINB, int ISO>
-__global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt, int pf_span, int dbg) {
+__global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt, int pf, int pfmode) {
   constexpr int G = 32 / LPW;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
-  // shared memory: [mbarrier 16 B][dummy body 48 B: the ground / world anchor, always zero]
-  //                [G x n x 6 doubles accumulators][G x LPW x 240 B staging]
-  const unsigned bar = s32(smraw);
+  // shared memory: [mbarrier rounds 8 B][mbarrier probes 8 B][dummy body 48 B: the ground / world
+  //                anchor, always zero][G x n x 6 doubles accumulators][64 B header + G x LPW x (32 + 208) B staging]
+  const unsigned bar = s32(smraw), bar2 = s32(smraw + 8);
   double* sb = reinterpret_cast<double*>(smraw + 64) + (size_t)sub * 6 * n;
   const int dummy = -(sub * n) - 1;            // body index of the dummy relative to this world's sb
-  unsigned char* stage = smraw + 64 + (size_t)G * 48 * n + (size_t)sub * LPW * RECB;
+  unsigned char* stage = smraw + 64 + (size_t)G * 48 * n;
   const unsigned stage_s = s32(stage);
   const double cfm = d.prm.cfm;
   const int nj = d.nj;
   const unsigned FULL = 0xffffffffu;
 
   if (lane == 0) {
-    mbar_init(bar, G);
+    mbar_init(bar, 1);
+    mbar_init(bar2, G);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (lane < 6) reinterpret_cast<double*>(smraw + 16)[lane] = 0.0;
-  const unsigned long long pol = policy_evict_first();
+  const unsigned long long pol = (pfmode & 2) ? policy_evict_last() : policy_evict_first();
   const unsigned long long pol_keep = policy_evict_last();
   double um = 0.0, uc = 0.0;                   // ISO == 2: the batch-wide (1/m, 1/c)
   if (ISO == 2) { um = d.minv_iso[0]; uc = d.minv_iso[1]; }
   __syncwarp();
-  unsigned parity = 0;
+  unsigned parity = 0, parity2 = 0;
   const int ngroups = (d.W + G - 1) / G;
 
   while (true) {
@@ -164,48 +353,53 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
     const double* maos = ISO ? d.minv_iso + (size_t)wc * (n + 1) * 2      // [n+1][2], row n = 0 (ground / world anchor)
                              : d.minv_aos + (size_t)wc * (n + 1) * 10;    // [n+1][10]
     const int nc = valid ? nj + d.c_count[wc] : 0;
-    const int ns = valid ? d.n_levels[wc] : 0;
-    char* recs = reinterpret_cast<char*>(d.rec + (size_t)wc * d.nrec * EGG_REC);
-    int cnt0 = 0;                                                 // blocks in stage 0
-    if (ns > 0) { const int* gls = d.level_start + (size_t)wc * (d.nrec + 1); cnt0 = gls[1] - gls[0]; }
+    char* gs = reinterpret_cast<char*>(d.rec) + (size_t)grp * group_stride_bytes(d.nrec, G);
+    const int R = d.grp_info[(size_t)grp * 4];                // rounds of the group
+    const int tot0 = d.grp_info[(size_t)grp * 4 + 1];         // blocks in round 0
+    const unsigned stream_bytes = (unsigned)d.grp_info[(size_t)grp * 4 + 2];
+    unsigned pf_pos = 0;                       // L2 prefetch cursor (bytes into the group stream)
+    double* lam_out = d.lam_out + (size_t)wc * 3 * d.nrec;
+    int* row_state = d.row_state + (size_t)wc * 3 * d.nrec;
     for (int i = sl; i < 6 * n; i += LPW) sb[i] = 0.0;
-
-    int ns_max = ns, nc_max = nc;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ns_max = max(ns_max, __shfl_xor_sync(FULL, ns_max, o));
-      nc_max = max(nc_max, __shfl_xor_sync(FULL, nc_max, o));
-    }
-    const int nchunk_max = (nc_max + LPW - 1) / LPW;
 
     bool active = nc > 0;
     double err = 0.0;
     int it = 0;
-    int probe_s0 = 0, probe_cnt = cnt0;        // the chunk whose residual is the cheap lower bound
+    unsigned probe_off = 0;                    // probe chunk: byte offset of its round in the group stream,
+    int probe_meta = 0;                        //   start | total << 8 | count << 16 of the world's blocks in that round
+    int probe_cnt = 0;
     double se = 0, s1 = 0, s2 = 0, s3 = 0;
     double best = -1.0;                        // exact pass: largest per-block contribution seen by this lane
-    int best_s0 = 0;
+    unsigned best_off = 0;
+    int best_meta = 0;
 
-    // chunk in flight (being copied / just landed) for this world
-    int c_s0 = 0, c_cnt = 0;
-    auto issue = [&](int s0, int cnt) {        // one round: every world leader arrives exactly once
-      c_s0 = s0; c_cnt = cnt;
+    auto issue_round = [&](unsigned off, int total) {        // one bulk copy feeds the whole warp-stage
+      if (lane == 0) {
+        const unsigned bytes = round_bytes(total);
+        mbar_arrive_tx(bar, bytes);
+        bulk_g2s(stage_s, gs + off, bytes, bar, pol);
+      }
+    };
+    auto issue_probe = [&](bool on) {                       // every world leader arrives exactly once
       if (sl == 0) {
-        if (cnt > 0) {
-          const unsigned bytes = (unsigned)cnt * RECB;
-          mbar_arrive_tx(bar, bytes);
-          bulk_g2s(stage_s, recs + (size_t)((dbg & 2) ? 0 : s0) * RECB, bytes, bar, pol);
+        if (on && probe_cnt > 0) {
+          // the world's multipliers and records of the probe round, into its own slices of the staging buffer
+          const int ps = probe_meta & 255, pt = (probe_meta >> 8) & 255;
+          mbar_arrive_tx(bar2, (unsigned)(BLKB * probe_cnt));
+          bulk_g2s(stage_s + HDRB + sub * (LPW * LAMB), gs + probe_off + HDRB + ps * LAMB, (unsigned)(LAMB * probe_cnt), bar2, pol);
+          bulk_g2s(stage_s + HDRB + 32 * LAMB + sub * (LPW * RECB), gs + probe_off + HDRB + pt * LAMB + ps * RECB, (unsigned)(RECB * probe_cnt), bar2, pol);
         } else {
-          mbar_arrive(bar);
+          mbar_arrive(bar2);
         }
       }
     };
 
     // One block on record v.  MODE_INIT: a = M^-1 J^T x0 (x0 = rhs, already in the record);
     // MODE_UPDATE: projected row-by-row update + impulse scatter; MODE_RESID: residual terms only.
-    auto step = [&](const double2* v, int mode, int slot, int chunk_s0) {
-      if (slot < 0) return;
-      const int i0 = __double2loint(IDX), i1 = __double2hiint(IDX);
+    auto step = [&](const double2* v, double x0, double x1, double x2, int mode, bool mine, unsigned lam_off, unsigned round_off, int round_meta, bool finalize) {
+      if (!mine) return;
+      const unsigned long long pk = (unsigned long long)__double_as_longlong(PKD);
+      const int i0 = (int)(pk & 1023u) - 1, i1 = (int)((pk >> 10) & 1023u) - 1;
       const int j0 = (i0 < 0) ? n : i0, j1 = (i1 < 0) ? n : i1;
       // accumulator pieces: (l.x,l.y) (l.z,a.x) (a.y,a.z); the ground / world side reads the
       // all-zero dummy body (never written: its stores are predicated off below)
@@ -226,7 +420,6 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           m1[2 * p] = t1.x; m1[2 * p + 1] = t1.y; m0[2 * p] = t0.x; m0[2 * p + 1] = t0.y;
         }
       }
-      const double x0 = LM0, x1 = LM1, x2 = LM2;
       double d0, d1, d2;
       if (mode == MODE_INIT) {
         d0 = x0; d1 = x1; d2 = x2;
@@ -239,7 +432,8 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         // e = rhs - (J a + cfm x) = -(A x - b) of the block's rows
         const double e0 = (RH0 - cfm * x0) - tx, e1 = (RH1 - cfm * x1) - ty, e2 = (RH2 - cfm * x2) - tz;
         if (mode == MODE_RESID) {
-          const bool eq = __double2loint(MET) < nj;
+          const int orig = (int)(pk >> 21);
+          const bool eq = orig < nj;
           const double q0s = e0 * e0, q1s = e1 * e1, q2s = e2 * e2;
           double c;
           if (eq) { c = q0s + q1s + q2s; se += c; }
@@ -251,11 +445,19 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
             s1 += c1; s2 += c2; s3 += c3;
             c = c1 + c2 + c3;
           }
-          if (c > best) { best = c; best_s0 = chunk_s0; }
+          if (c > best) { best = c; best_off = round_off; best_meta = round_meta; }
+          if (finalize) {                          // read-only pass over x_k: leave the taps in reference row order
+            double* lo = lam_out + 3 * orig;
+            int* rs = row_state + 3 * orig;
+            lo[0] = x0; lo[1] = x1; lo[2] = x2;
+            rs[0] = eq ? 3 : (x0 == -1.0 ? 1 : (x0 == 1.0 ? 2 : 0));
+            rs[1] = eq ? 3 : (x1 == -1.0 ? 1 : (x1 == 1.0 ? 2 : 0));
+            rs[2] = eq ? 3 : (x2 == 0.0 ? 1 : 0);
+          }
           return;
         }
         // clamp kind of this block (q2 shift already folded in by the assembly kernel)
-        const bool contact = __double2hiint(MET) == KIND_CONTACT;
+        const bool contact = ((pk >> 20) & 1u) == KIND_CONTACT;
         const double lo01 = contact ? -1.0 : -kInf, hi01 = contact ? 1.0 : kInf, lo2 = contact ? 0.0 : -kInf;
         double n0 = x0 + e0 * IA0;
         n0 = fmin(fmax(n0, lo01), hi01);
@@ -266,8 +468,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         double n2 = x2 + ((e2 - DO1 * d0) - DO2 * d1) * IA2;
         n2 = fmax(n2, lo2);
         d2 = n2 - x2;
-        double* lp = reinterpret_cast<double*>(recs + (size_t)slot * RECB) + REC_DDIAG;
-        if (!(dbg & 1)) { lp[0] = n0; lp[1] = n1; lp[2] = n2; }
+        st_sector(reinterpret_cast<double*>(gs + lam_off), n0, n1, n2, 0.0);
       }
       // impulse scatter: a += M^-1 J^T delta
       const double ix = RC0 * d0 + RC3 * d1 + RC6 * d2, iy = RC1 * d0 + RC4 * d1 + RC7 * d2, iz = RC2 * d0 + RC5 * d1 + RC8 * d2;
@@ -300,81 +501,95 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
       }
     };
 
-    if (__any_sync(FULL, active)) {
+    if (R > 0 && __any_sync(FULL, active)) {
       const double tol = d.prm.tol;
       const int k_max = d.prm.k_max;
       // One loop runs every phase (a single copy of the block code):
-      //   PH_INIT   x0 = rhs scattered into the accumulator, stage by stage
-      //   PH_PROBE  residual terms of one chunk: the cheap lower bound of the residual of x_k
-      //   PH_EXACT  residual of x_k over consecutive LPW-slices of all blocks (read-only)
-      //   PH_UPDATE sweep k -> k+1, stage by stage (next count from the staged record)
-      // The first chunk of a phase is in flight when the phase starts; nothing is in flight when
-      // PH_EXACT / PH_UPDATE end.
+      //   PH_INIT   x0 = rhs scattered into the accumulator, round by round
+      //   PH_PROBE  residual terms of one chunk per world: the cheap lower bound of the residual of x_k
+      //   PH_EXACT  residual of x_k over all rounds (read-only; writes the lam_out / row_state taps)
+      //   PH_UPDATE sweep k -> k+1, round by round
+      // Round 0 is in flight when a round phase starts; nothing is in flight when it ends.
       int phase = PH_INIT, k = 0;
       bool need_exact = false;
-      issue(0, active ? cnt0 : 0);
+      issue_round(0, tot0);
       while (true) {
+        const bool probe = (phase == PH_PROBE);
         const int mode = (phase == PH_INIT) ? MODE_INIT : (phase == PH_UPDATE ? MODE_UPDATE : MODE_RESID);
-        const int nsteps = (phase == PH_PROBE) ? 1 : (phase == PH_EXACT ? nchunk_max : ns_max);
         const bool on = (phase == PH_EXACT) ? need_exact : active;
-        const bool staged = (phase == PH_INIT || phase == PH_UPDATE);
-        double2 buf[EGG_PIECES];
+        const int nsteps = probe ? 1 : R;
+        unsigned roff = 0;
+        double2 buf[SPIECES];
         for (int t = 0; t < nsteps; t++) {
-          mbar_wait(bar, parity);
-          parity ^= 1u;
-          const int s0 = c_s0, cnt = c_cnt;
-          const int slot = (sl < cnt) ? s0 + sl : -1;
-          int nxt = 0;
-          if (cnt > 0) nxt = *reinterpret_cast<const int*>(stage + 29 * 8);   // broadcast read of record 0's spare slot
-          if (slot >= 0) {
-            const double2* sp = reinterpret_cast<const double2*>(stage) + sl * EGG_PIECES;
+          int start, total = 0, nxt = 0, cnt;
+          if (probe) {                             // the world's own chunk, in its slice of the staging buffer
+            mbar_wait(bar2, parity2);
+            parity2 ^= 1u;
+            start = sub * LPW;
+            cnt = probe_cnt;
+          } else {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            start = stage[sub]; total = stage[G]; nxt = stage[HDR_NEXT];
+            cnt = (int)stage[sub + 1] - start;
+          }
+          const bool mine = on && sl < cnt;
+          const unsigned cur_off = probe ? probe_off : roff;
+          const int cur_meta = probe ? probe_meta : (start | (total << 8) | (cnt << 16));
+          if (phase == PH_INIT && t == 0) { probe_off = 0; probe_meta = cur_meta; probe_cnt = cnt; }   // first probe: the world's stage 0
+          double x0 = 0, x1 = 0, x2 = 0;
+          if (mine) {
+            const double2* lq = reinterpret_cast<const double2*>(stage + HDRB) + (start + sl) * 2;
+            const double2* sp = reinterpret_cast<const double2*>(stage + HDRB + (probe ? 32 : total) * LAMB) + (start + sl) * SPIECES;
+            const double2 la = lq[0], lb = lq[1];
+            x0 = la.x; x1 = la.y; x2 = lb.x;
 #pragma unroll
-            for (int p = 0; p < EGG_PIECES; p++) buf[p] = sp[p];
+            for (int p = 0; p < SPIECES; p++) buf[p] = sp[p];
           }
           __syncwarp();                            // staging buffer free again
-          if (t + 1 < nsteps) {
-            if (staged) issue(s0 + cnt, (on && t + 1 < ns) ? nxt : 0);
-            else { const int b0 = (t + 1) * LPW; issue(b0, on ? max(0, min(LPW, nc - b0)) : 0); }
+          const unsigned roff_next = roff + round_bytes(total);
+          if (probe) {
+            issue_round(0, tot0);                  // speculate "continue": round 0 streams in meanwhile
+          } else if (t + 1 < R) {
+            issue_round(roff_next, nxt);
           }
-          if (cnt > 0 && phase != PH_PROBE && pf_span > 0) {
-            // HBM -> L2 prefetch in spans of 2^pf_span bytes.  Random ~1 KB reads reach only about
-            // half of the HBM bandwidth (tools/micro/dram_chunk_bench: 3.4 TB/s at 960 B, 5.4 at
-            // 3840 B, 7.0 at 7680 B), so DRAM is asked for whole spans: when the consumer enters
-            // span i the lanes of the world prefetch span i+2 (cyclically: the next sweep streams
-            // the same records again); the 1 KB stage copies then hit L2.
-            const int sp_now = ((s0 + cnt) * RECB - 1) >> pf_span;
-            const int sp_prev = (s0 * RECB - 1) >> pf_span;          // -1 >> k = -1: the first chunk enters span 0
-            if (sp_now != sp_prev) {
-              const int nspan = ((nc * RECB - 1) >> pf_span) + 1;
-              int tgt = sp_now + 2;
-              if (tgt >= nspan) tgt -= nspan;
-              if (tgt >= nspan) tgt = nspan - 1;
-              const int lines = 1 << (pf_span - 7);
-              const char* base = recs + ((size_t)tgt << pf_span);
-              const int lim = nc * RECB - (tgt << pf_span);          // bytes left in the world's records
-              for (int q = sl; q < lines && q * 128 < lim; q += LPW) prefetch_l2(base + q * 128);
+          if (!probe && pf > 0) {
+            // HBM -> L2 prefetch cursor kept pf x 4 KB ahead of the consumer (one 128-byte line per
+            // lane and span; the cursor wraps: the next sweep streams the same bytes again).  The
+            // loaded DRAM latency is ~2-3 us (tools/micro/dram_chunk_bench), one 4 KB round per
+            // warp in flight cannot cover it.
+            int lead = (int)pf_pos - (int)roff_next;
+            if (lead < 0) lead += (int)stream_bytes;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+              if (lead < pf * 4096) {
+                if (!(pfmode & 1)) {
+                  const unsigned a = pf_pos + lane * 128;
+                  if (a < stream_bytes) prefetch_l2(gs + a);
+                } else if ((pfmode & 1) && lane == 0) {
+                  bulk_prefetch_l2(gs + pf_pos, min(4096u, stream_bytes - pf_pos));
+                }
+                pf_pos += 4096;
+                lead += 4096;
+                if (pf_pos >= stream_bytes) pf_pos = 0;
+              }
             }
           }
-          step(buf, mode, slot, s0);
-          __syncwarp();                            // accumulator writes visible to the next stage
+          step(buf, x0, x1, x2, mode, mine, cur_off + HDRB + (unsigned)(((cur_meta & 255) + sl) * LAMB), cur_off, cur_meta, !probe);
+          __syncwarp();                            // accumulator writes visible to the next round
+          roff = roff_next;
         }
-        // ---- phase transitions (warp-uniform) ----
-        if (phase == PH_PROBE) {
-          // speculate "continue": stage 0 of the sweep streams in while the bound is reduced
-          issue(0, active ? cnt0 : 0);
+        if (probe) {
           reduce4();
           const double lb = sqrt(se) + (sqrt(s1) + sqrt(s2) + sqrt(s3));
           need_exact = active && !(lb > 2.0 * tol);
-          if (!__any_sync(FULL, need_exact)) { phase = PH_UPDATE; if (active) ++it; continue; }
-          mbar_wait(bar, parity);                  // rare: drain the speculative copy, evaluate exactly
-          parity ^= 1u;
-          __syncwarp();
-          phase = PH_EXACT;
           se = s1 = s2 = s3 = 0.0;
           best = -1.0;
-          issue(0, need_exact ? min(LPW, nc) : 0);
+          if (!__any_sync(FULL, need_exact)) { phase = PH_UPDATE; if (active) ++it; }
+          else phase = PH_EXACT;                   // rare; the round-0 copy in flight serves it as well
           continue;
         }
+        // ---- phase transitions (warp-uniform) ----
         if (phase == PH_EXACT) {
           reduce4();
           if (need_exact) {
@@ -383,18 +598,20 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           }
           // move the probe to the chunk with the largest contribution
           double bb = best;
-          int bs = best_s0;
+          unsigned bo = best_off;
+          int bc = best_meta;
 #pragma unroll
           for (int o = LPW / 2; o > 0; o >>= 1) {
             const double ob = __shfl_xor_sync(FULL, bb, o);
-            const int os = __shfl_xor_sync(FULL, bs, o);
-            if (ob > bb || (ob == bb && os < bs)) { bb = ob; bs = os; }
+            const unsigned oo = __shfl_xor_sync(FULL, bo, o);
+            const int oc = __shfl_xor_sync(FULL, bc, o);
+            if (ob > bb || (ob == bb && oo < bo)) { bb = ob; bo = oo; bc = oc; }
           }
-          if (need_exact && bb > 0.0) { probe_s0 = bs; probe_cnt = min(LPW, nc - bs); }
+          if (need_exact && bb > 0.0) { probe_off = bo; probe_meta = bc; probe_cnt = bc >> 16; }
           if (!__any_sync(FULL, active)) break;
           phase = PH_UPDATE;
           if (active) ++it;
-          issue(0, active ? cnt0 : 0);
+          issue_round(0, tot0);
           continue;
         }
         if (phase == PH_UPDATE) {
@@ -406,42 +623,25 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         // after PH_INIT (k = 0) or PH_UPDATE: start the check of x_k
         se = s1 = s2 = s3 = 0.0;
         best = -1.0;
-        if (k < k_max) {
+        if (k < k_max && __any_sync(FULL, active && probe_cnt > 0)) {
           phase = PH_PROBE;
-          issue(probe_s0, active ? probe_cnt : 0);
+          issue_probe(active);
         } else {
           phase = PH_EXACT;
           need_exact = active;
-          issue(0, need_exact ? min(LPW, nc) : 0);
+          issue_round(0, tot0);
         }
       }
     }
     __syncwarp();
 
     if (valid) {
-      double* lo_out = d.lam_out + (size_t)w * 3 * d.nrec;
-      int* rs_out = d.row_state + (size_t)w * 3 * d.nrec;
-      for (int s = sl; s < nc; s += LPW) {
-        const double* rp = reinterpret_cast<const double*>(recs + (size_t)s * RECB);
-        const int orig = __double2loint(rp[REC_META]);
-        const bool eq = orig < nj;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          const double x = __ldcg(rp + REC_DDIAG + c);
-          lo_out[3 * orig + c] = x;
-          int state = 0;
-          if (eq) state = 3;
-          else if (x == ((c < 2) ? -1.0 : 0.0)) state = 1;
-          else if (c < 2 && x == 1.0) state = 2;
-          rs_out[3 * orig + c] = state;
-        }
-      }
       if (sl == 0) {
         int* stt = d.stats + (size_t)w * 8;
         stt[4] = it;
         stt[5] = 0;
         stt[6] = (cfm != 0.0);
-        stt[7] = ns;
+        stt[7] = d.n_levels[w];
         d.resid[w] = err;
       }
       // v' = v + dt (M^-1 f + a); p += dt (v+v')/2; R <- WtoQ((w+w')/2, dt) R  (ensembles.cc:535,572-591)
@@ -496,7 +696,7 @@ int env_i(const char* name, int dflt) {
 template <int LPW, int MINB, int ISO>
 void launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
-  const size_t smem = 64 + (size_t)G * (48 * d.n + LPW * RECB);
+  const size_t smem = 64 + HDRB + 32 + (size_t)G * (48 * d.n + LPW * BLKB);
   cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -509,14 +709,14 @@ void launch(const EggDev& d, double dt, cudaStream_t s) {
   const int groups = (d.W + G - 1) / G;
   const int grid = groups < sms * per_sm ? groups : sms * per_sm;
   cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
-  egg_pgs_stream_kernel<LPW, MINB, ISO><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF_SPAN", PF_SPAN), env_i("EGG_PGS_DBG", 0));
+  egg_pgs_stream_kernel<LPW, MINB, ISO><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 0), env_i("EGG_PGS_PFMODE", 2));
 }
 
-// LPW = lanes per world = maximum blocks per stage the assembly emitted.  Registers are allocated
-// per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler = 168 registers.
+// Registers are allocated per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler
+// = 168 registers.
 template <int MINB, int ISO>
-void launch_lpw(const EggDev& d, double dt, int lpw, cudaStream_t s) {
-  switch (lpw) {
+void launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
+  switch (d.lpw) {
     case 1: launch<1, MINB, ISO>(d, dt, s); break;
     case 2: launch<2, MINB, ISO>(d, dt, s); break;
     case 4: launch<4, MINB, ISO>(d, dt, s); break;
@@ -524,10 +724,40 @@ void launch_lpw(const EggDev& d, double dt, int lpw, cudaStream_t s) {
     default: launch<8, MINB, ISO>(d, dt, s); break;
   }
 }
+
 }  // namespace
 
-void egg_launch_solve_pgs_stream(const EggDev& d, double dt, int lpw, cudaStream_t s) {
-  if (d.iso == 2) launch_lpw<12, 2>(d, dt, lpw, s);
-  else if (d.iso == 1) launch_lpw<12, 1>(d, dt, lpw, s);
-  else launch_lpw<8, 0>(d, dt, lpw, s);
+size_t egg_stream_rec_bytes(int W, int nrec, int lpw) {
+  const int G = 32 / lpw;
+  return (size_t)((W + G - 1) / G) * group_stride_bytes(nrec, G);
+}
+
+// Group-stream assembly: schedule (per world) -> rounds (per group) -> records (per world).
+void egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s) {
+  const int G = 32 / d.lpw;
+  {
+    const size_t per = ((size_t)(d.n + 4 * d.nrec + 2 + 7) & ~(size_t)7) * sizeof(unsigned short);
+    int wpc = (int)((size_t)200 * 1024 / per);
+    if (wpc > 4) wpc = 4;
+    if (wpc < 1) wpc = 1;
+    const size_t smem = wpc * per;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_schedule_kernel<<<(d.W + wpc - 1) / wpc, 128, smem, s>>>(d, d.lpw, wpc);
+  }
+  const int ngroups = (d.W + G - 1) / G;
+  egg_rounds_kernel<<<(ngroups + 3) / 4, 128, 0, s>>>(d, G);
+  const size_t smem = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double);
+  if (d.nrec <= 128) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_records_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_records_kernel<64><<<d.W, 64, smem, s>>>(d, dt, G);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_records_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    egg_records_kernel<256><<<d.W, 256, smem, s>>>(d, dt, G);
+  }
+}
+
+void egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s) {
+  if (d.iso == 2) launch_lpw<12, 2>(d, dt, s);
+  else if (d.iso == 1) launch_lpw<12, 1>(d, dt, s);
+  else launch_lpw<8, 0>(d, dt, s);
 }
