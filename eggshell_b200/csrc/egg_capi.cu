@@ -440,7 +440,7 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     else if (solver == EGG_SOLVER_DENSE_MURTY) egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes);
     else egg_launch_solve_iter(b->dev, dt, solver, b->stream);
     if (b->profiling) CK(cudaEventRecord(e[3], b->stream));
-    b->launches += 3;
+    b->launches += (solver == EGG_SOLVER_PGS && b->dev.rec_fmt) ? 5 : 3;   // collide, assemble (1 or 3 kernels), solve
   }
   CK(cudaGetLastError());
   return EGG_OK;

@@ -32,8 +32,8 @@
 //     also writes them out in reference row order (lam_out / row_state taps).
 //   * World groups are handed out by an atomic counter.
 //
-// Per warp: 64 B + G x n x 48 B accumulators + 96 B + G x LPW x 240 B staging.  64-body worlds:
-// 20128 B -> 11 resident warps of 4 worlds per SM at 168 registers.
+// Per warp: 64 B + G x n x 48 B accumulators + 64 B + G x LPW x 240 B staging.  64-body worlds:
+// 20096 B -> 11 resident warps of 4 worlds per SM at 168 registers.
 //
 // Replaces: sparse::GaussSeidelIteration + GetResidualError + the velocity/position update, i.e.
 // /root/reference/eggshell/sparse_iterations.cc:148-226,51-69,
@@ -696,7 +696,7 @@ int env_i(const char* name, int dflt) {
 template <int LPW, int MINB, int ISO>
 void launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
-  const size_t smem = 64 + HDRB + 32 + (size_t)G * (48 * d.n + LPW * BLKB);
+  const size_t smem = 64 + HDRB + (size_t)G * (48 * d.n + LPW * BLKB);   // 20096 B for 64 bodies: 11 CTAs per SM
   cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -709,7 +709,7 @@ void launch(const EggDev& d, double dt, cudaStream_t s) {
   const int groups = (d.W + G - 1) / G;
   const int grid = groups < sms * per_sm ? groups : sms * per_sm;
   cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
-  egg_pgs_stream_kernel<LPW, MINB, ISO><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 0), env_i("EGG_PGS_PFMODE", 2));
+  egg_pgs_stream_kernel<LPW, MINB, ISO><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3), env_i("EGG_PGS_PFMODE", 0));
 }
 
 // Registers are allocated per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler

@@ -65,6 +65,72 @@ def test_legged_pgs_joints_and_contacts():
     print("legged worst", worst)
 
 
+def test_pgs_general_and_mixed_inertia_paths():
+    """The three M^-1 layouts of the stream kernel against the oracle: general 3x3 inverse inertia
+    (anisotropic bodies), isotropic but different per body, and the EGG_OPT_EXACT_INERTIA switch."""
+    import eggshell_b200 as E
+    rng = np.random.default_rng(5)
+    # (a) anisotropic inertia -> general kernel
+    scene = E.scenes.cairn(9, rocks=5, zb=(0.1, 0.6), seed=21)
+    scene["I"] = np.tile(np.diag([0.01, 0.02, 0.03]), (9, 5, 1, 1))
+    worst = _stepwise(scene, 12, list(range(9)), dict(solver=E.SOLVER_PGS), dict(solver=1))
+    print("anisotropic worst", worst)
+    # (b) isotropic, masses and inertias differ per body -> per-body (1/m, 1/c) loads
+    scene = E.scenes.cairn(9, rocks=5, zb=(0.1, 0.6), seed=22)
+    scene["m"] = rng.uniform(0.5, 2.0, size=scene["m"].shape)
+    scene["I"] = np.eye(3) * rng.uniform(0.05, 0.2, size=(9, 5, 1, 1))
+    worst = _stepwise(scene, 12, list(range(9)), dict(solver=E.SOLVER_PGS), dict(solver=1))
+    print("isotropic non-uniform worst", worst)
+    # (c) uniform cubes with the inverse inertia kept exactly as computed (no snapping)
+    scene = E.scenes.cairn(9, rocks=5, zb=(0.1, 0.6), seed=23)
+    worst = _stepwise(scene, 12, list(range(9)), dict(solver=E.SOLVER_PGS, quirks=E.QUIRKS_REFERENCE | 4), dict(solver=1))
+    print("exact inertia worst", worst)
+
+
+def test_pgs_converging_worlds_take_the_exact_residual_path():
+    """Worlds that converge before k_max: the probe lower bound fails, the exact residual decides;
+    the sweep count must be the oracle's (checked inside _stepwise) and at least one world must
+    actually have stopped early."""
+    import eggshell_b200 as E
+    scene = E.scenes.cairn(13, rocks=2, xb=(-1.0, 1.0), yb=(-1.0, 1.0), zb=(0.12, 0.16), seed=31)
+    scene["v"] *= 0.05
+    scene["w"] *= 0.05
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS)
+    b.step(scene["dt"])
+    sw = b.status()["sweeps"]
+    b.close()
+    assert ((sw > 0) & (sw < 500)).any(), f"no world converged early: {sw}"
+    worst = _stepwise(scene, 6, list(range(13)), dict(solver=E.SOLVER_PGS), dict(solver=1))
+    print("converging worst", worst, "sweeps of step 0", sw.tolist())
+
+
+@pytest.mark.parametrize("name,W,k_max", [("pile64", 6, 40), ("stack10", 37, 200), ("legged20", 11, 100)])
+def test_pgs_stream_matches_legacy_variant(name, W, k_max, monkeypatch):
+    """The default 'stream' kernel (group-interleaved records, probe-based stopping test) against
+    the earlier 'fast' kernel (per-world records, residual every sweep) on the same scenes, with
+    world counts that do not fill the last warp group: same sweep counts and clamp states,
+    multipliers and state within 1e-9."""
+    import eggshell_b200 as E
+    scene = getattr(E.scenes, name)(W)
+    res = {}
+    for variant in ("stream", "fast"):
+        monkeypatch.setenv("EGG_PGS_VARIANT", variant)
+        b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, taps=True)
+        out = []
+        for s in range(2):
+            b.step(scene["dt"])
+            st, con = b.status(), b.contacts()
+            out.append((st["sweeps"].copy(), con["row_state"].copy(), con["lam"].copy(), [x.copy() for x in b.bodies()], st["residual"].copy()))
+        b.close()
+        res[variant] = out
+    for a, c in zip(res["stream"], res["fast"]):
+        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
+        assert rel_err(a[2], c[2]) < 1e-9
+        for x, y in zip(a[3], c[3]):
+            assert rel_err(x, y) < 1e-9
+        assert rel_err(a[4], c[4], floor=1e-3) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------
 # Against the committed golden fixtures (tests/golden/*.npz).
 def _vs_golden(name, scene, nw, ns, batch_kw, tol=1e-9):
