@@ -334,7 +334,16 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
     load_box(sp, sR, sside, n, i, b1);
     load_box(sp, sR, sside, n, j, b2);
     Sat s;
-    hit[q] = sat_test(b1, b2, s) ? 1 : 0;
+    // Conservative cull in front of the SAT (the reference's own broadphase,
+    // toolkit/collision.cc:58-109, is unused by Ensemble::UpdateContacts): boxes whose bounding
+    // spheres are apart by a 1e-3 relative margin are disjoint, so one of the 15 axes separates
+    // them by a margin far above rounding and CollideBoxes returns false (collision.cc:218,249).
+    // The colliding-pair list is unchanged (tests/test_gpu_parity.py::test_broadphase_cull_keeps_pair_list);
+    // EGG_OPT_NO_BROADPHASE_CULL (quirks bit 8) runs the SAT on every pair.
+    const d3 dc = b2.c - b1.c;
+    const double rr = norm3(b1.h) + norm3(b2.h);
+    const bool apart = !(d.prm.quirks & 8) && dot3(dc, dc) > rr * rr * 1.002;
+    hit[q] = (!apart && sat_test(b1, b2, s)) ? 1 : 0;
     if (d.pair_code) { d.pair_code[(size_t)w * P + q] = 0; d.pair_cnt[(size_t)w * P + q] = 0; }
   }
   __syncthreads();

@@ -1046,7 +1046,13 @@ int egg_stage_cap(const EggDev& d) {
   int lpw = env_int("EGG_PGS_LPW", 0);
   if (pgs_variant(d) == 4) {
     // narrow worlds expose little parallelism per level: fewer lanes, more worlds per warp
-    if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 1 : (d.n <= 24 ? 4 : 8);   // measured: stack10 87 ms at 1 / 101 at 2 / 133 at 4; legged20 95 ms at 4 / 115 at 2 / 123 at 8
+    // (measured: stack10 87 ms at 1 / 101 at 2 / 133 at 4; legged20 95 ms at 4 / 115 at 2 / 123 at 8)
+    // -- unless the batch is too small to give every SM a few warps that way
+    if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16) {
+      lpw = (d.n <= 12) ? 1 : (d.n <= 24 ? 4 : 8);
+      const long long want = (long long)num_sms() * env_int("EGG_PGS_MIN_WARPS_PER_SM", 4);
+      while (lpw < 8 && (long long)d.W * lpw / 32 < want) lpw *= 2;
+    }
     return lpw;
   }
   if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16 && lpw != 32) lpw = 8;

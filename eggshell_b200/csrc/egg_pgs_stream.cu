@@ -143,7 +143,7 @@ __device__ __forceinline__ void st_sector(double* p, double a, double b, double 
 constexpr int HDRB = 64;      // round header bytes (keeps the multiplier sectors 32-byte aligned)
 // bytes of a round with `total` blocks: header, multipliers, records, padded to a sector
 __host__ __device__ inline unsigned round_bytes(int total) { return (unsigned)(HDRB + BLKB * total + 31) & ~31u; }
-constexpr int HDR_NEXT = 40;  // byte: total blocks of the next round (cyclic)
+constexpr int HDR_NEXT = 40;  // bytes 40, 41: total blocks of the next round and of the one after (cyclic)
 
 __host__ __device__ inline size_t group_stride_bytes(int nrec, int G) { return ((size_t)nrec * ((size_t)BLKB * G + HDRB + 32) + 255) & ~(size_t)255; }
 
@@ -232,7 +232,8 @@ __global__ void __launch_bounds__(128) egg_rounds_kernel(EggDev d, int G) {
         if (w < d.W && t < d.n_levels[w]) tot += d.st_cnt[(size_t)w * nrec + t];
       }
       hdr[G] = (unsigned char)tot;
-      hdr[HDR_NEXT] = (unsigned char)total_of(t + 1 == R ? 0 : t + 1);
+      hdr[HDR_NEXT] = (unsigned char)total_of((t + 1) % R);
+      hdr[HDR_NEXT + 1] = (unsigned char)total_of((t + 2) % R);
     }
     const unsigned bytes = (t < R) ? round_bytes(tot) : 0u;
     unsigned incl = bytes;
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(128) egg_rounds_kernel(EggDev d, int G) {
     gi[0] = R;
     gi[1] = (R > 0) ? total_of(0) : 0;
     gi[2] = (int)base;
-    gi[3] = 0;
+    gi[3] = (R > 0) ? total_of(1 % R) : 0;
   }
 }
 
@@ -312,24 +313,29 @@ enum { PH_INIT = 0, PH_PROBE = 1, PH_EXACT = 2, PH_UPDATE = 3 };
 // inverse inertias, see egg_solve.cu) and comes as one 16-byte load per body.  ISO == 2: all
 // bodies of the batch share the same (1/m, 1/c) (every body of the reference is the same cube,
 // body.h:91) and the pair is a kernel constant.
-template <int LPW, int MINB, int ISO>
+// NBUF: staging buffers = rounds in flight (2 where shared memory allows: a stage's copy has ~1 us
+// of latency even from L2, narrow worlds are bound by exactly that round trip).
+template <int LPW, int MINB, int ISO, int NBUF>
 __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt, int pf, int pfmode) {
   constexpr int G = 32 / LPW;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
-  // shared memory: [mbarrier rounds 8 B][mbarrier probes 8 B][dummy body 48 B: the ground / world
+  // shared memory: [mbarrier probes 8 B][mbarrier rounds, buffer 0, 8 B][dummy body 48 B: the ground / world
   //                anchor, always zero][G x n x 6 doubles accumulators][64 B header + G x LPW x (32 + 208) B staging]
-  const unsigned bar = s32(smraw), bar2 = s32(smraw + 8);
+  const unsigned bar2 = s32(smraw), bar = s32(smraw + 8);
   double* sb = reinterpret_cast<double*>(smraw + 64) + (size_t)sub * 6 * n;
   const int dummy = -(sub * n) - 1;            // body index of the dummy relative to this world's sb
-  unsigned char* stage = smraw + 64 + (size_t)G * 48 * n;
-  const unsigned stage_s = s32(stage);
+  constexpr int STG = HDRB + 32 * BLKB;        // one staging buffer: header + 32 blocks
+  unsigned char* stage0 = smraw + 64 + (size_t)G * 48 * n;
+  const unsigned stage_s = s32(stage0);
+  const unsigned bar_b1 = s32(stage0 + NBUF * STG);   // round barrier of buffer 1 (NBUF == 2), behind the staging buffers
   const double cfm = d.prm.cfm;
   const int nj = d.nj;
   const unsigned FULL = 0xffffffffu;
 
   if (lane == 0) {
     mbar_init(bar, 1);
+    if (NBUF == 2) mbar_init(bar_b1, 1);
     mbar_init(bar2, G);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -373,12 +379,18 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
     unsigned best_off = 0;
     int best_meta = 0;
 
-    auto issue_round = [&](unsigned off, int total) {        // one bulk copy feeds the whole warp-stage
+    auto issue_round = [&](unsigned off, int total, int b) {   // one bulk copy feeds the whole warp-stage
       if (lane == 0) {
         const unsigned bytes = round_bytes(total);
-        mbar_arrive_tx(bar, bytes);
-        bulk_g2s(stage_s, gs + off, bytes, bar, pol);
+        const unsigned br = (NBUF == 2 && b) ? bar_b1 : bar;
+        mbar_arrive_tx(br, bytes);
+        bulk_g2s(stage_s + (NBUF == 2 ? b * STG : 0), gs + off, bytes, br, pol);
       }
+    };
+    const int tot1 = d.grp_info[(size_t)grp * 4 + 3];         // blocks in round 1 (= round 0 when R == 1)
+    auto start_rounds = [&]() {                               // the first NBUF rounds of a pass
+      issue_round(0, tot0, 0);
+      if (NBUF == 2 && R > 1) issue_round(round_bytes(tot0), tot1, 1);
     };
     auto issue_probe = [&](bool on) {                       // every world leader arrives exactly once
       if (sl == 0) {
@@ -512,7 +524,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
       // Round 0 is in flight when a round phase starts; nothing is in flight when it ends.
       int phase = PH_INIT, k = 0;
       bool need_exact = false;
-      issue_round(0, tot0);
+      start_rounds();
       while (true) {
         const bool probe = (phase == PH_PROBE);
         const int mode = (phase == PH_INIT) ? MODE_INIT : (phase == PH_UPDATE ? MODE_UPDATE : MODE_RESID);
@@ -521,16 +533,19 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         unsigned roff = 0;
         double2 buf[SPIECES];
         for (int t = 0; t < nsteps; t++) {
-          int start, total = 0, nxt = 0, cnt;
+          int start, total = 0, nxt = 0, nxt2 = 0, cnt;
+          const unsigned char* stage = stage0;
           if (probe) {                             // the world's own chunk, in its slice of the staging buffer
             mbar_wait(bar2, parity2);
             parity2 ^= 1u;
             start = sub * LPW;
             cnt = probe_cnt;
           } else {
-            mbar_wait(bar, parity);
-            parity ^= 1u;
-            start = stage[sub]; total = stage[G]; nxt = stage[HDR_NEXT];
+            const int b = (NBUF == 2) ? (t & 1) : 0;
+            stage = stage0 + b * STG;
+            mbar_wait(b ? bar_b1 : bar, (parity >> b) & 1u);
+            parity ^= 1u << b;
+            start = stage[sub]; total = stage[G]; nxt = stage[HDR_NEXT]; nxt2 = stage[HDR_NEXT + 1];
             cnt = (int)stage[sub + 1] - start;
           }
           const bool mine = on && sl < cnt;
@@ -549,9 +564,11 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           __syncwarp();                            // staging buffer free again
           const unsigned roff_next = roff + round_bytes(total);
           if (probe) {
-            issue_round(0, tot0);                  // speculate "continue": round 0 streams in meanwhile
+            start_rounds();                        // speculate "continue": the first rounds stream in meanwhile
+          } else if (NBUF == 2) {
+            if (t + 2 < R) issue_round(roff_next + round_bytes(nxt), nxt2, t & 1);
           } else if (t + 1 < R) {
-            issue_round(roff_next, nxt);
+            issue_round(roff_next, nxt, 0);
           }
           if (!probe && pf > 0) {
             // HBM -> L2 prefetch cursor kept pf x 4 KB ahead of the consumer (one 128-byte line per
@@ -611,7 +628,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           if (!__any_sync(FULL, active)) break;
           phase = PH_UPDATE;
           if (active) ++it;
-          issue_round(0, tot0);
+          start_rounds();
           continue;
         }
         if (phase == PH_UPDATE) {
@@ -629,7 +646,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         } else {
           phase = PH_EXACT;
           need_exact = active;
-          issue_round(0, tot0);
+          start_rounds();
         }
       }
     }
@@ -693,36 +710,44 @@ int env_i(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int LPW, int MINB, int ISO>
+template <int LPW, int MINB, int ISO, int NBUF>
 void launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
-  const size_t smem = 64 + HDRB + (size_t)G * (48 * d.n + LPW * BLKB);   // 20096 B for 64 bodies: 11 CTAs per SM
-  cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = 64 + (size_t)G * 48 * d.n + (size_t)NBUF * (HDRB + 32 * BLKB) + (NBUF == 2 ? 16 : 0);   // NBUF 1, 64 bodies: 20096 B, 11 CTAs per SM
+  cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO>, 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF>, 32, smem);
   if (per_sm < 1) per_sm = 1;
   const int cap = env_i("EGG_PGS_CTAS_PER_SM", 0);
   if (cap > 0 && cap < per_sm) per_sm = cap;
   const int groups = (d.W + G - 1) / G;
   const int grid = groups < sms * per_sm ? groups : sms * per_sm;
   cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
-  egg_pgs_stream_kernel<LPW, MINB, ISO><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3), env_i("EGG_PGS_PFMODE", 0));
+  egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3), env_i("EGG_PGS_PFMODE", 0));
 }
 
 // Registers are allocated per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler
 // = 168 registers.
-template <int MINB, int ISO>
+template <int MINB, int ISO, int NBUF>
 void launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
   switch (d.lpw) {
-    case 1: launch<1, MINB, ISO>(d, dt, s); break;
-    case 2: launch<2, MINB, ISO>(d, dt, s); break;
-    case 4: launch<4, MINB, ISO>(d, dt, s); break;
-    case 16: launch<16, MINB, ISO>(d, dt, s); break;
-    default: launch<8, MINB, ISO>(d, dt, s); break;
+    case 1: launch<1, MINB, ISO, NBUF>(d, dt, s); break;
+    case 2: launch<2, MINB, ISO, NBUF>(d, dt, s); break;
+    case 4: launch<4, MINB, ISO, NBUF>(d, dt, s); break;
+    case 16: launch<16, MINB, ISO, NBUF>(d, dt, s); break;
+    default: launch<8, MINB, ISO, NBUF>(d, dt, s); break;
   }
+}
+template <int MINB, int ISO>
+void launch_nbuf(const EggDev& d, double dt, cudaStream_t s) {
+  // two rounds in flight where the accumulators leave room (narrow worlds: the solve is bound by
+  // the round trip of a stage copy); wide worlds keep one buffer and 11 resident warps
+  const int nbuf = env_i("EGG_PGS_NBUF", d.n <= 32 ? 2 : 1);
+  if (nbuf == 2) launch_lpw<MINB, ISO, 2>(d, dt, s);
+  else launch_lpw<MINB, ISO, 1>(d, dt, s);
 }
 
 }  // namespace
@@ -757,7 +782,7 @@ void egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s) {
 }
 
 void egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s) {
-  if (d.iso == 2) launch_lpw<12, 2>(d, dt, s);
-  else if (d.iso == 1) launch_lpw<12, 1>(d, dt, s);
-  else launch_lpw<8, 0>(d, dt, s);
+  if (d.iso == 2) launch_nbuf<12, 2>(d, dt, s);
+  else if (d.iso == 1) launch_nbuf<12, 1>(d, dt, s);
+  else launch_nbuf<8, 0>(d, dt, s);
 }

@@ -51,7 +51,10 @@ enum egg_quirk {
   /* Not a reference quirk: keep (R I_b R^T)^-1 exactly as computed (ensembles.cc:210).  By default
    * egg_init snaps a numerically isotropic inverse inertia (|dev| <= 1e-13 relative; every body of
    * the reference's own scenes) to c^-1 I3, which lets the PGS kernel keep 2 doubles per body. */
-  EGG_OPT_EXACT_INERTIA = 4
+  EGG_OPT_EXACT_INERTIA = 4,
+  /* Not a reference quirk: run the 15-axis SAT on every body pair.  By default pairs whose bounding
+   * spheres are clearly apart are culled first (conservative: the colliding-pair list is unchanged). */
+  EGG_OPT_NO_BROADPHASE_CULL = 8
 };
 #define EGG_QUIRKS_REFERENCE 3
 

@@ -250,10 +250,10 @@ def test_full_size_c3_contact_counts_and_capacity():
 
 # ---------------------------------------------------------------------------------------------
 # Dense path (what the reference ships): Schur complement + Murty principal pivoting.
-def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-6, **kw):
+def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-6, oracle_kw=None, **kw):
     import eggshell_b200 as E
     b = E.scenes.make_batch(scene, solver=E.SOLVER_DENSE_MURTY, taps=True, **kw)
-    ows = [oracle_world(scene, wi, solver=0)[0] for wi in worlds_idx]
+    ows = [oracle_world(scene, wi, solver=0, **(oracle_kw or {}))[0] for wi in worlds_idx]
     dt = scene["dt"]
     npiv = 0
     for s in range(nsteps):
@@ -318,6 +318,45 @@ def test_dense_cairn_and_chain_stepwise():
     npiv = _stepwise_dense(E.scenes.cairn(8, rocks=4, zb=(0.2, 0.5), seed=21), 25, list(range(8)))
     assert npiv > 0
     _stepwise_dense(E.scenes.chain(2, links=6, anchor=(0.0, 0.0, 0.25), seed=5, anchor_jitter=0.05), 6, [0, 1])
+
+
+def test_broadphase_cull_keeps_pair_list():
+    """the bounding-sphere cull in front of the all-pairs SAT must not change the
+    colliding set: pair list (with codes and per-pair counts), contact list and geometry are
+    bit-identical with and without it, on piles, stacks, chains and loose random boxes."""
+    import eggshell_b200 as E
+    scenes = [E.scenes.pile64(6), E.scenes.stack10(16), E.scenes.legged20(8),
+              E.scenes.cairn(32, rocks=12, xb=(-0.4, 0.4), yb=(-0.4, 0.4), zb=(0.1, 0.9), seed=3)]
+    for scene in scenes:
+        out = []
+        for quirks in (E.QUIRKS_REFERENCE, E.QUIRKS_REFERENCE | 8):
+            b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=30, taps=True, quirks=quirks)
+            res = []
+            for s in range(3):
+                b.step(scene["dt"])
+                ph, con = b.pair_hits(), b.contacts()
+                res.append((ph, con))
+            b.close()
+            out.append(res)
+        nh = 0
+        for (pa, ca), (pb, cb) in zip(*out):
+            for k in pa:
+                assert np.array_equal(pa[k], pb[k]), (scene["name"], k)
+            for k in ("count", "i0", "i1", "code", "pos", "nrm", "depth"):
+                assert np.array_equal(ca[k], cb[k]), (scene["name"], k)
+            nh += int(np.sum(pa["n"]))
+        print(scene["name"], "pair hits compared:", nh)
+
+
+def test_dense_box_bounds_honoured():
+    """the dense path with the BOX friction bounds actually applied (the reference
+    drops them, lcp.cc:298 = quirk q1; toolkit/lcp.cc:380-785 is its bounded Murty).  Bounded
+    principal pivoting on the device against the oracle's bounded solver: same pivots, same
+    active set (rows at lo / hi), state within 1e-9."""
+    import eggshell_b200 as E
+    q = E.QUIRK_GS_BOUNDS_SHIFT   # q1 off
+    npiv = _stepwise_dense(E.scenes.cairn(8, rocks=4, zb=(0.2, 0.5), seed=21), 25, list(range(8)), quirks=q, oracle_kw=dict(quirks=q))
+    assert npiv > 0
 
 
 def test_cpp_host_mirror_demo():
