@@ -743,9 +743,10 @@ void launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
 }
 template <int MINB, int ISO>
 void launch_nbuf(const EggDev& d, double dt, cudaStream_t s) {
-  // two rounds in flight where the accumulators leave room (narrow worlds: the solve is bound by
-  // the round trip of a stage copy); wide worlds keep one buffer and 11 resident warps
-  const int nbuf = env_i("EGG_PGS_NBUF", d.n <= 32 ? 2 : 1);
+  // EGG_PGS_NBUF=2 keeps two rounds in flight.  Measured no better anywhere (stack10 4096 worlds
+  // 26.9 vs 26.2 ms, legged20 106 vs 90 ms, pile64 8.8 vs 8.1 ms): the stage copy is not what
+  // bounds narrow worlds, the ~300-instruction dependent stage is.  One buffer is the default.
+  const int nbuf = env_i("EGG_PGS_NBUF", 1);
   if (nbuf == 2) launch_lpw<MINB, ISO, 2>(d, dt, s);
   else launch_lpw<MINB, ISO, 1>(d, dt, s);
 }
