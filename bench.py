@@ -196,6 +196,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL_DEBUG=VERSION prints "NCCL version ..." on stdout; rank 0's stdout must be ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     fn, kw, Wd, desc = WORKLOADS[args.workload]

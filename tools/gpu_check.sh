@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -s -k "broadphase or box_bounds" > gpurun_out/pytest_gpu_new.log 2>&1; tail -n 8 gpurun_out/pytest_gpu_new.log
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -n 4 gpurun_out/pytest_gpu.log
-timeout 300 python tools/profile_run.py c3 16384 20 3 2>&1 | tail -n 1
+nvidia-smi -L
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 > gpurun_out/bench_n2_r1g.json 2> gpurun_out/bench_n2_r1g.err
+echo "rc=$?"; tail -c 600 gpurun_out/bench_n2_r1g.json; tail -n 15 gpurun_out/bench_n2_r1g.err
