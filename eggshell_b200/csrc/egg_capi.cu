@@ -432,13 +432,24 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
       }
       CK(cudaEventRecord(e[0], b->stream));
     }
+    // EGG_SYNC_DEBUG=1: synchronise after every kernel and name the one that failed
+    static const bool dbg_sync = getenv("EGG_SYNC_DEBUG") && atoi(getenv("EGG_SYNC_DEBUG")) != 0;
+#define DBG_SYNC(what)                                                                       \
+  if (dbg_sync) {                                                                            \
+    cudaError_t e__ = cudaStreamSynchronize(b->stream);                                      \
+    if (e__ != cudaSuccess) { set_err(what, e__); return EGG_ERR_CUDA; }                      \
+  }
     egg_launch_collide(b->dev, b->stream);
+    DBG_SYNC("egg_collide_kernel")
     if (b->profiling) CK(cudaEventRecord(e[1], b->stream));
     egg_launch_assemble(b->dev, dt, b->stream);
+    DBG_SYNC("assembly kernels")
     if (b->profiling) CK(cudaEventRecord(e[2], b->stream));
     if (solver == EGG_SOLVER_PGS) egg_launch_solve_pgs(b->dev, dt, b->stream);
     else if (solver == EGG_SOLVER_DENSE_MURTY) egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes);
     else egg_launch_solve_iter(b->dev, dt, solver, b->stream);
+    DBG_SYNC("solve kernel")
+#undef DBG_SYNC
     if (b->profiling) CK(cudaEventRecord(e[3], b->stream));
     b->launches += (solver == EGG_SOLVER_PGS && b->dev.rec_fmt) ? 5 : 3;   // collide, assemble (1 or 3 kernels), solve
   }

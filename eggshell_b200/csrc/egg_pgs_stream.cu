@@ -412,6 +412,9 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
       if (!mine) return;
       const unsigned long long pk = (unsigned long long)__double_as_longlong(PKD);
       const int i0 = (int)(pk & 1023u) - 1, i1 = (int)((pk >> 10) & 1023u) - 1;
+      // range guard: a record that is not a record must never become an address (three compares per
+      // block; the world is flagged EGG_ST_INTERNAL instead)
+      if (i0 >= n || i1 >= n || (int)(pk >> 21) >= d.nrec) { atomicOr(&d.status[wc], 64); return; }
       const int j0 = (i0 < 0) ? n : i0, j1 = (i1 < 0) ? n : i1;
       // accumulator pieces: (l.x,l.y) (l.z,a.x) (a.y,a.z); the ground / world side reads the
       // all-zero dummy body (never written: its stores are predicated off below)
@@ -547,6 +550,10 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
             parity ^= 1u << b;
             start = stage[sub]; total = stage[G]; nxt = stage[HDR_NEXT]; nxt2 = stage[HDR_NEXT + 1];
             cnt = (int)stage[sub + 1] - start;
+            if (total > 32 || nxt > 32 || nxt2 > 32 || cnt < 0 || cnt > LPW || start + cnt > total) {   // same guard for the header
+              if (sl == 0 && valid) atomicOr(&d.status[wc], 64);
+              cnt = 0; total = min(total, 32); nxt = min(nxt, 32); nxt2 = min(nxt2, 32);
+            }
           }
           const bool mine = on && sl < cnt;
           const unsigned cur_off = probe ? probe_off : roff;
@@ -561,6 +568,11 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
 #pragma unroll
             for (int p = 0; p < SPIECES; p++) buf[p] = sp[p];
           }
+          // The staging buffer is handed back to the TMA unit here: the loads above are generic-proxy
+          // reads, the next copy is an async-proxy write, and only this fence orders the two (the role
+          // the release semantics of the consumer's mbarrier arrive play in a producer / consumer
+          // pipeline).
+          __threadfence_block();
           __syncwarp();                            // staging buffer free again
           const unsigned roff_next = roff + round_bytes(total);
           if (probe) {

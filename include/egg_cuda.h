@@ -66,7 +66,9 @@ enum egg_status {
   EGG_ST_BAD_INIT = 4,          /* ensembles.cc:27 CHECK_MSG would fail */
   EGG_ST_CONTACT_OVERFLOW = 8,  /* more contacts than max_contacts; the tail was dropped */
   EGG_ST_NONFINITE = 16,        /* NaN/Inf reached the state */
-  EGG_ST_DENSE_OVERFLOW = 32    /* more rows than the dense path is provisioned for; lambda = 0 */
+  EGG_ST_DENSE_OVERFLOW = 32,   /* more rows than the dense path is provisioned for; lambda = 0 */
+  EGG_ST_INTERNAL = 64          /* a staged constraint record failed its range check inside the solve kernel (never expected;
+                                   the block is skipped instead of dereferencing a bad index) */
 };
 
 /* Compile-time constants of the reference gathered into one POD (SURVEY.md §5 "Config"):
