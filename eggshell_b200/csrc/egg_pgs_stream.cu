@@ -645,7 +645,9 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         }
         if (phase == PH_UPDATE) {
           // multipliers were written with generic stores; the async proxy reads them back next sweep
-          asm volatile("fence.proxy.async;" ::: "memory");
+          // (.global: the multipliers live in global memory; the space-less form also emits MEMBAR.ALL.GPU)
+          if (pfmode & 16) asm volatile("fence.proxy.async;" ::: "memory");
+          else asm volatile("fence.proxy.async.global;" ::: "memory");
           __syncwarp();
           ++k;
         }
