@@ -155,7 +155,7 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   }
   {
     // record format 1 (multipliers inside the record) belongs to the default "stream" PGS variant;
-    // EGG_PGS_VARIANT=mw|mwpf|fused|fast|tma selects one of the measured alternatives (format 0)
+    // EGG_PGS_VARIANT=fast selects the earlier per-world-record kernel (format 0)
     const char* pv = getenv("EGG_PGS_VARIANT");
     d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS && (!pv || pv[0] == 's')) ? 1 : 0;
   }
