@@ -1,5 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -n 3 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 1 | cut -c 1-200
-timeout 300 python tools/compare_variants.py c3 64 50 3 stream fast | tail -n 1
+timeout 900 python -m pytest tests -m gpu -x -q -k "dense or host_mirror or stabilize" > gpurun_out/pytest_gpu_dense.log 2>&1; tail -n 3 gpurun_out/pytest_gpu_dense.log
+timeout 600 python tools/dense_run.py 1024 3 2>&1 | tail -n 4
