@@ -158,6 +158,9 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
     // EGG_PGS_VARIANT=fast selects the earlier per-world-record kernel (format 0)
     const char* pv = getenv("EGG_PGS_VARIANT");
     d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS && (!pv || pv[0] == 's')) ? 1 : 0;
+    // the group-stream assembly keeps u16 level tables of 2 (n + 4 nrec) bytes per world in shared
+    // memory: beyond ~24 k constraint slots per world the per-world-record kernel takes over
+    if (d.nrec > 24000) d.rec_fmt = 0;
   }
   if (d.rec_fmt) {
     // group stream of the default PGS variant: G = 32 / lpw worlds share one interleaved record stream
