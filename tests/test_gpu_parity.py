@@ -248,6 +248,25 @@ def test_full_size_c3_contact_counts_and_capacity():
     b.close(); b2.close()
 
 
+@pytest.mark.parametrize("name,W,k_max,steps", [("pile64", 65536, 500, 1), ("pile64", 16384, 5, 3), ("stack10", 65536, 100, 2), ("legged20", 131072, 100, 2)])
+def test_full_size_pgs_runs_clean(name, W, k_max, steps):
+    """Full occupancy (11 resident warps per SM, several world groups per warp), long and short
+    solves: no world may end non-finite or with an internal flag, every world of a scene sees the
+    same number of sweeps at these non-converging settings, and the multipliers stay bounded."""
+    import eggshell_b200 as E
+    scene = getattr(E.scenes, name)(W)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, max_contacts=1024 if name == "pile64" else 0)
+    for s in range(steps):
+        b.step(scene["dt"])
+        st = b.status()
+        assert int(np.bitwise_or.reduce(st["status"])) == 0, (s, np.nonzero(st["status"])[0][:16].tolist())
+        assert np.isfinite(st["residual"]).all()
+    p, R, v, w = b.bodies()
+    assert np.isfinite(p).all() and np.isfinite(R).all() and np.isfinite(v).all() and np.isfinite(w).all()
+    assert float(np.abs(v).max()) < 1e3 and float(np.abs(w).max()) < 1e4
+    b.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # Dense path (what the reference ships): Schur complement + Murty principal pivoting.
 def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-6, oracle_kw=None, **kw):

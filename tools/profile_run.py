@@ -18,4 +18,15 @@ for s in range(steps):
     st = b.status()
     print(f"step {s}: kernel ms narrow/assemble/solve = {ms[0]:.3f} {ms[1]:.3f} {ms[2]:.3f}; contacts {st['n_contacts'].mean():.1f} "
           f"sweeps {st['sweeps'].mean():.1f} status_or {int(np.bitwise_or.reduce(st['status']))}", flush=True)
+bad = np.nonzero(b.status()['status'])[0]
+if len(bad):
+    print('worlds with status != 0:', len(bad), bad[:32].tolist(), 'status values', np.unique(b.status()['status'][bad]).tolist())
+    p, R, v, w = b.bodies()
+    con = b.contacts()
+    for wb in bad[:4]:
+        nf = lambda a: np.nonzero(~np.isfinite(a.reshape(a.shape[0], -1)).all(axis=1))[0].tolist()[:12]
+        print(' world', wb, 'nonfinite p', nf(p[wb]), 'R', nf(R[wb]), 'v', nf(v[wb]), 'w', nf(w[wb]), 'max|v|', float(np.nanmax(np.abs(v[wb]))), 'max|w|', float(np.nanmax(np.abs(w[wb]))),
+              'lam nonfinite', int((~np.isfinite(con['lam'][wb])).sum()), 'max|lam|', float(np.nanmax(np.abs(con['lam'][wb]))), 'count', int(con['count'][wb]))
+    good = np.setdiff1d(np.arange(W), bad)[:1]
+    print(' a good world', good, 'max|v|', float(np.abs(v[good]).max()), 'max|lam|', float(np.abs(con['lam'][good]).max()))
 b.close()
