@@ -568,11 +568,15 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
 #pragma unroll
             for (int p = 0; p < SPIECES; p++) buf[p] = sp[p];
           }
-          // The staging buffer is handed back to the TMA unit here: the loads above are generic-proxy
-          // reads, the next copy is an async-proxy write, and only this fence orders the two (the role
-          // the release semantics of the consumer's mbarrier arrive play in a producer / consumer
-          // pipeline).
-          __threadfence_block();
+          // The staging buffer is handed back to the TMA unit here.  The loads above are generic-proxy
+          // reads, the next copy is an async-proxy write: the two proxies are ordered only by a
+          // cross-proxy fence.  A generic fence (__threadfence_block) is NOT enough: with it (or with
+          // nothing) the next round could land under loads that had not been performed yet and the
+          // lanes worked on the wrong round's blocks -- rare at 4 worlds per warp, 1-2 % of the
+          // worlds per step at 32 worlds per warp and >= 2 resident CTAs per SM, found with
+          // tools/determinism_check.py (bit-for-bit repeatability of a full-size step) and pinned
+          // down by switching the fence at run time inside one binary.
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();                            // staging buffer free again
           const unsigned roff_next = roff + round_bytes(total);
           if (probe) {

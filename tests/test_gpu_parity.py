@@ -267,6 +267,32 @@ def test_full_size_pgs_runs_clean(name, W, k_max, steps):
     b.close()
 
 
+@pytest.mark.parametrize("name,W,k_max,lpw", [("stack10", 65536, 10, "1"), ("stack10", 65536, 10, ""), ("pile64", 16384, 5, ""), ("pile64", 8192, 5, "16"), ("legged20", 131072, 10, "")])
+def test_full_size_step_is_bit_reproducible(name, W, k_max, lpw, monkeypatch):
+    """The kernels are deterministic, so the same full-size step from the same state must give the
+    same bits every time.  This is the test that exposes ordering bugs between the shared-memory
+    loads of a stage and the TMA copy of the next one (a generic fence instead of the cross-proxy
+    fence made 1-2 % of the worlds differ from run to run at 32 worlds per warp)."""
+    import eggshell_b200 as E
+    if lpw:
+        monkeypatch.setenv("EGG_PGS_LPW", lpw)
+    scene = getattr(E.scenes, name)(W)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, max_contacts=1024 if name == "pile64" else 0)
+    b.snapshot()
+    ref = None
+    for r in range(3):
+        b.restore()
+        b.step(scene["dt"])
+        out = [x.copy() for x in b.bodies()] + [b.contacts()["lam"].copy()]
+        assert int(np.bitwise_or.reduce(b.status()["status"])) == 0
+        if ref is None:
+            ref = out
+            continue
+        for a, c in zip(out, ref):
+            assert np.array_equal(a.view(np.uint64), c.view(np.uint64)), f"run {r} differs from run 0"
+    b.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # Dense path (what the reference ships): Schur complement + Murty principal pivoting.
 def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-6, oracle_kw=None, **kw):
