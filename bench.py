@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="32 = opt-in FP32 constraint records (not the headline)")
     return ap.parse_args()
 
 
@@ -207,7 +208,7 @@ def run_ours(args):
     n, nj, dt = scene["n"], scene["nj"], scene["dt"]
     maxc = {"c3": 1024}.get(args.workload, 0)
     horizon = HORIZON.get(args.workload, 1)
-    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=args.k_max, max_contacts=maxc, device=local)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=args.k_max, max_contacts=maxc, device=local, precision=args.precision)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
     costs = torch.zeros(W, dtype=torch.float64, device="cuda")
@@ -304,7 +305,8 @@ def run_ours(args):
         # chunks, round headers and extra exact-residual passes are NOT counted: a lower bound).
         blocks_w = st["n_rows"].astype(np.float64) / 3.0
         sweeps_w = st["sweeps"].astype(np.float64)
-        stream_bytes = float((blocks_w * ((sweeps_w + 2.0) * ROW_STREAM_BYTES + sweeps_w * 32.0)).sum())
+        row_bytes = ROW_STREAM_BYTES if args.precision == 64 else 144.0   # 112 B record + 32 B multipliers
+        stream_bytes = float((blocks_w * ((sweeps_w + 2.0) * row_bytes + sweeps_w * 32.0)).sum())
         solve_bytes = W * bytes_step + stream_bytes
         achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
         traffic = None
@@ -341,7 +343,7 @@ def run_ours(args):
         line = {
             "metric": "world-steps/sec", "value": value, "unit": "world-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f64 arithmetic, f32 constraint records", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "worlds_per_gpu": W, "bodies": n, "joints": nj,
                        "solver": "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01, "dt": dt, "horizon": horizon, "parallelism": f"worlds sharded x{world}",
                        "step": "every timed step = egg_restore(scene state, D2D) + egg_step: all steps do the same work",

@@ -100,7 +100,7 @@ class Batch:
 
     def __init__(self, n_worlds, n_bodies, n_joints=0, *, solver=SOLVER_DENSE_MURTY, k_max=500, tol=1e-9,
                  cfm=0.01, erp=0.2, gravity=(0.0, 0.0, -9.8), min_constraint_dist=1e-6, max_contacts=0,
-                 quirks=QUIRKS_REFERENCE, cfm_mode=CFM_AUTO, device=0, taps=False):
+                 quirks=QUIRKS_REFERENCE, cfm_mode=CFM_AUTO, device=0, taps=False, precision=64):
         L = lib()
         d = EggDesc()
         _chk(L.egg_desc_default(C.byref(d), n_worlds, n_bodies, n_joints), "egg_desc_default")
@@ -108,6 +108,7 @@ class Batch:
         d.gravity[0], d.gravity[1], d.gravity[2] = gravity
         d.min_constraint_dist, d.max_contacts = min_constraint_dist, max_contacts
         d.quirks, d.cfm_mode, d.device, d.taps = quirks, cfm_mode, device, int(taps)
+        d.precision = int(precision)   # 64, or 32 = FP32 constraint records in the PGS stream (opt-in)
         self.h = C.c_void_p()
         _chk(L.egg_create(C.byref(d), C.byref(self.h)), "egg_create")
         self.W, self.n, self.nj = n_worlds, n_bodies, n_joints

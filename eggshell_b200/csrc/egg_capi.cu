@@ -103,7 +103,8 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   if (!dsc || !out) return EGG_ERR_ARG;
   *out = nullptr;
   if (dsc->n_worlds <= 0 || dsc->n_bodies <= 0 || dsc->n_joints < 0 || dsc->n_bodies > 360) { g_err = "bad shape"; return EGG_ERR_ARG; }
-  if (dsc->precision != 64) { g_err = "only FP64 is implemented"; return EGG_ERR_UNSUPPORTED; }
+  if (dsc->precision != 64 && dsc->precision != 32) { g_err = "precision must be 64 or 32"; return EGG_ERR_ARG; }
+  if (dsc->precision == 32 && dsc->solver != EGG_SOLVER_PGS) { g_err = "precision = 32 (FP32 constraint records) exists for the PGS solver only"; return EGG_ERR_UNSUPPORTED; }
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -161,10 +162,12 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
     // the group-stream assembly keeps u16 level tables of 2 (n + 4 nrec) bytes per world in shared
     // memory: beyond ~24 k constraint slots per world the per-world-record kernel takes over
     if (d.nrec > 24000) d.rec_fmt = 0;
+    if (dsc->precision == 32 && !d.rec_fmt) { g_err = "precision = 32 needs the default (stream) PGS kernel"; return EGG_ERR_UNSUPPORTED; }
   }
   if (d.rec_fmt) {
     // group stream of the default PGS variant: G = 32 / lpw worlds share one interleaved record stream
     d.lpw = egg_stage_cap(d);
+    d.blkb = egg_stream_blkb(dsc->precision);
     const int groups = (W + 32 / d.lpw - 1) / (32 / d.lpw);
     DA(d.rec, egg_stream_rec_bytes(W, d.nrec, d.lpw) / sizeof(double));
     DA(d.c_pos, (size_t)W * d.nrec);

@@ -79,6 +79,7 @@ struct EggDev {
   int* iso_flag;              // [1] device: 1 while every body seen by egg_init was isotropic
   int iso;                    // host copy of iso_flag, valid after the first step following egg_init
   // group-stream assembly of the default PGS variant (egg_pgs_stream.cu)
+  int blkb;                   // stream bytes per block: 32 (multipliers) + 208 (FP64 record) or 112 (precision = 32 record)
   int lpw;                    // lanes per world = stage cap; G = 32 / lpw worlds share a warp and a record stream
   int* c_pos;                 // [W][nrec] stage << 8 | index inside the stage, per constraint
   unsigned char* st_cnt;      // [W][nrec] blocks per stage
@@ -134,6 +135,7 @@ void egg_launch_solve_pgs_fast(const EggDev& d, double dt, int lpw, cudaStream_t
 void egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s);
 void egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s);
 size_t egg_stream_rec_bytes(int W, int nrec, int lpw);
+int egg_stream_blkb(int precision);
 int egg_stage_cap(const EggDev& d);
 void egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s);
 void egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s);

@@ -47,11 +47,14 @@
 namespace {
 
 #define kInf CUDART_INF
-constexpr int SREC = 26;            // doubles per stream record (see the layout below)
-constexpr int RECB = SREC * 8;      // 208 = 13 x 16 B: conflict-free 128-bit shared-memory reads at this stride
-constexpr int SPIECES = SREC / 2;   // 16-byte pieces
+// Two record formats (layouts below): FP64 records of 26 doubles = 208 B = 13 x 16 B, and the opt-in
+// precision = 32 format of 24 floats + the packed word = 112 B = 7 x 16 B (both odd multiples of
+// 16 B: conflict-free 128-bit shared-memory reads at these strides).
+constexpr int SREC = 26;            // doubles per FP64 stream record
+constexpr int RECB64 = SREC * 8;    // 208
+constexpr int RECB32 = 112;
 constexpr int LAMB = 32;            // bytes of one block's multipliers (3 doubles + pad = one sector)
-constexpr int BLKB = RECB + LAMB;   // stream bytes per block
+constexpr int BLKB_MAX = RECB64 + LAMB;   // stream bytes per block, FP64 records (allocation bound)
 
 __device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned bar, int count) {
@@ -108,32 +111,34 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
 // the scattered 32-byte stores alone cost 40 % of the stream: tools/micro/stream_bench measures
 // 4.1 TB/s with them against 6.2 read-only and 5.6 with the compact array; and partial-sector
 // stores additionally made L2 fetch every sector it merged: +8 GB reads per launch, profiles/r1f.)
-// As double2 pieces v[13]:
-#define RC0 v[0].x
-#define RC1 v[0].y
-#define RC2 v[1].x
-#define RC3 v[1].y
-#define RC4 v[2].x
-#define RC5 v[2].y
-#define RC6 v[3].x
-#define RC7 v[3].y
-#define RC8 v[4].x
-#define R0X v[4].y
-#define R0Y v[5].x
-#define R0Z v[5].y
-#define R1X v[6].x
-#define R1Y v[6].y
-#define R1Z v[7].x
-#define DO0 v[7].y
-#define DO1 v[8].x
-#define DO2 v[8].y
-#define IA0 v[9].x
-#define IA1 v[9].y
-#define IA2 v[10].x
-#define RH0 v[10].y
-#define RH1 v[11].x
-#define RH2 v[11].y
-#define PKD v[12].x
+// precision = 32 record (112 B): the same 24 numbers as floats (96 B), then the packed word and 8
+// spare bytes.  The kernel widens them to double as it reads; multipliers, accumulators and all
+// arithmetic stay FP64.
+// Inside the kernel the 24 numbers of either format are fld[0..23]:
+#define RC0 fld[0]
+#define RC1 fld[1]
+#define RC2 fld[2]
+#define RC3 fld[3]
+#define RC4 fld[4]
+#define RC5 fld[5]
+#define RC6 fld[6]
+#define RC7 fld[7]
+#define RC8 fld[8]
+#define R0X fld[9]
+#define R0Y fld[10]
+#define R0Z fld[11]
+#define R1X fld[12]
+#define R1Y fld[13]
+#define R1Z fld[14]
+#define DO0 fld[15]
+#define DO1 fld[16]
+#define DO2 fld[17]
+#define IA0 fld[18]
+#define IA1 fld[19]
+#define IA2 fld[20]
+#define RH0 fld[21]
+#define RH1 fld[22]
+#define RH2 fld[23]
 
 __device__ __forceinline__ void st_sector(double* p, double a, double b, double c, double e) {   // one aligned 32-byte store
   asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(e) : "memory");
@@ -142,10 +147,10 @@ __device__ __forceinline__ void st_sector(double* p, double a, double b, double 
 
 constexpr int HDRB = 64;      // round header bytes (keeps the multiplier sectors 32-byte aligned)
 // bytes of a round with `total` blocks: header, multipliers, records, padded to a sector
-__host__ __device__ inline unsigned round_bytes(int total) { return (unsigned)(HDRB + BLKB * total + 31) & ~31u; }
+__host__ __device__ inline unsigned round_bytes(int total, int blkb) { return (unsigned)(HDRB + blkb * total + 31) & ~31u; }
 constexpr int HDR_NEXT = 40;  // bytes 40, 41: total blocks of the next round and of the one after (cyclic)
 
-__host__ __device__ inline size_t group_stride_bytes(int nrec, int G) { return ((size_t)nrec * ((size_t)BLKB * G + HDRB + 32) + 255) & ~(size_t)255; }
+__host__ __device__ inline size_t group_stride_bytes(int nrec, int G) { return ((size_t)nrec * ((size_t)BLKB_MAX * G + HDRB + 32) + 255) & ~(size_t)255; }
 
 // ---------------------------------------------------------------------------------------------
 // Assembly 1/3: dependency levels and stages of one world (one warp per world, lane 0 scans).
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(128) egg_rounds_kernel(EggDev d, int G) {
       hdr[HDR_NEXT] = (unsigned char)total_of((t + 1) % R);
       hdr[HDR_NEXT + 1] = (unsigned char)total_of((t + 2) % R);
     }
-    const unsigned bytes = (t < R) ? round_bytes(tot) : 0u;
+    const unsigned bytes = (t < R) ? round_bytes(tot, d.blkb) : 0u;
     unsigned incl = bytes;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
@@ -287,22 +292,37 @@ __global__ void __launch_bounds__(NT) egg_records_kernel(EggDev d, double dt, in
     const int p = cp[c], stg = p >> 8, idx = p & 255;
     const unsigned ro = roff[stg];
     const unsigned start = gs[ro + sub];
-    double o[SREC];
-#pragma unroll
-    for (int q = 0; q < 18; q++) o[q] = v[q];                       // Rc, r0, r1, D off-diagonal
-#pragma unroll
-    for (int q = 0; q < 3; q++) { o[18 + q] = v[REC_INVA + q]; o[21 + q] = v[REC_RHS + q]; }
     const int kind = __double2hiint(v[REC_META]);
     const unsigned long long pk = (unsigned long long)(i0 + 1) | ((unsigned long long)(i1 + 1) << 10) | ((unsigned long long)kind << 20) | ((unsigned long long)c << 21);
-    o[24] = __longlong_as_double((long long)pk);
-    o[25] = 0.0;
     const unsigned total = gs[ro + G];
     double2* lam = reinterpret_cast<double2*>(gs + ro + HDRB + (size_t)LAMB * (start + idx));
     lam[0] = make_double2(v[REC_RHS], v[REC_RHS + 1]);              // x0 = rhs
     lam[1] = make_double2(v[REC_RHS + 2], 0.0);
-    double2* out = reinterpret_cast<double2*>(gs + ro + HDRB + (size_t)LAMB * total + (size_t)RECB * (start + idx));
+    const int recb = d.blkb - LAMB;
+    unsigned char* rp = gs + ro + HDRB + (size_t)LAMB * total + (size_t)recb * (start + idx);
+    if (recb == RECB64) {
+      double o[SREC];
 #pragma unroll
-    for (int q = 0; q < SPIECES; q++) out[q] = make_double2(o[2 * q], o[2 * q + 1]);
+      for (int q = 0; q < 18; q++) o[q] = v[q];                     // Rc, r0, r1, D off-diagonal
+#pragma unroll
+      for (int q = 0; q < 3; q++) { o[18 + q] = v[REC_INVA + q]; o[21 + q] = v[REC_RHS + q]; }
+      o[24] = __longlong_as_double((long long)pk);
+      o[25] = 0.0;
+      double2* out = reinterpret_cast<double2*>(rp);
+#pragma unroll
+      for (int q = 0; q < SREC / 2; q++) out[q] = make_double2(o[2 * q], o[2 * q + 1]);
+    } else {
+      // precision = 32: the constraint data in FP32 (multipliers, accumulators and arithmetic stay FP64)
+      float o[24];
+#pragma unroll
+      for (int q = 0; q < 18; q++) o[q] = (float)v[q];
+#pragma unroll
+      for (int q = 0; q < 3; q++) { o[18 + q] = (float)v[REC_INVA + q]; o[21 + q] = (float)v[REC_RHS + q]; }
+      float4* out = reinterpret_cast<float4*>(rp);
+#pragma unroll
+      for (int q = 0; q < 6; q++) out[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      reinterpret_cast<double2*>(rp)[6] = make_double2(__longlong_as_double((long long)pk), 0.0);
+    }
   }
 }
 
@@ -315,9 +335,12 @@ enum { PH_INIT = 0, PH_PROBE = 1, PH_EXACT = 2, PH_UPDATE = 3 };
 // body.h:91) and the pair is a kernel constant.
 // NBUF: staging buffers = rounds in flight (2 where shared memory allows: a stage's copy has ~1 us
 // of latency even from L2, narrow worlds are bound by exactly that round trip).
-template <int LPW, int MINB, int ISO, int NBUF>
+template <int LPW, int MINB, int ISO, int NBUF, bool F32>
 __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt, int pf, int pfmode) {
   constexpr int G = 32 / LPW;
+  constexpr int RECB = F32 ? RECB32 : RECB64;   // bytes of one staged record
+  constexpr int SPIECES = RECB / 16;
+  constexpr int BLKB = RECB + LAMB;
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
   // shared memory: [mbarrier probes 8 B][mbarrier rounds, buffer 0, 8 B][dummy body 48 B: the ground / world
@@ -381,7 +404,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
 
     auto issue_round = [&](unsigned off, int total, int b) {   // one bulk copy feeds the whole warp-stage
       if (lane == 0) {
-        const unsigned bytes = round_bytes(total);
+        const unsigned bytes = round_bytes(total, BLKB);
         const unsigned br = (NBUF == 2 && b) ? bar_b1 : bar;
         mbar_arrive_tx(br, bytes);
         bulk_g2s(stage_s + (NBUF == 2 ? b * STG : 0), gs + off, bytes, br, pol);
@@ -390,7 +413,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
     const int tot1 = d.grp_info[(size_t)grp * 4 + 3];         // blocks in round 1 (= round 0 when R == 1)
     auto start_rounds = [&]() {                               // the first NBUF rounds of a pass
       issue_round(0, tot0, 0);
-      if (NBUF == 2 && R > 1) issue_round(round_bytes(tot0), tot1, 1);
+      if (NBUF == 2 && R > 1) issue_round(round_bytes(tot0, BLKB), tot1, 1);
     };
     auto issue_probe = [&](bool on) {                       // every world leader arrives exactly once
       if (sl == 0) {
@@ -410,7 +433,20 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
     // MODE_UPDATE: projected row-by-row update + impulse scatter; MODE_RESID: residual terms only.
     auto step = [&](const double2* v, double x0, double x1, double x2, int mode, bool mine, unsigned lam_off, unsigned round_off, int round_meta, bool finalize) {
       if (!mine) return;
-      const unsigned long long pk = (unsigned long long)__double_as_longlong(PKD);
+      double fld[24];
+      unsigned long long pk;
+      if (F32) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) {
+          const float2 lo = *reinterpret_cast<const float2*>(&v[q].x), hi = *reinterpret_cast<const float2*>(&v[q].y);
+          fld[4 * q] = (double)lo.x; fld[4 * q + 1] = (double)lo.y; fld[4 * q + 2] = (double)hi.x; fld[4 * q + 3] = (double)hi.y;
+        }
+        pk = (unsigned long long)__double_as_longlong(v[6].x);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 12; q++) { fld[2 * q] = v[q].x; fld[2 * q + 1] = v[q].y; }
+        pk = (unsigned long long)__double_as_longlong(v[12].x);
+      }
       const int i0 = (int)(pk & 1023u) - 1, i1 = (int)((pk >> 10) & 1023u) - 1;
       // range guard: a record that is not a record must never become an address (three compares per
       // block; the world is flagged EGG_ST_INTERNAL instead)
@@ -578,11 +614,11 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           // down by switching the fence at run time inside one binary.
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();                            // staging buffer free again
-          const unsigned roff_next = roff + round_bytes(total);
+          const unsigned roff_next = roff + round_bytes(total, BLKB);
           if (probe) {
             start_rounds();                        // speculate "continue": the first rounds stream in meanwhile
           } else if (NBUF == 2) {
-            if (t + 2 < R) issue_round(roff_next + round_bytes(nxt), nxt2, t & 1);
+            if (t + 2 < R) issue_round(roff_next + round_bytes(nxt, BLKB), nxt2, t & 1);
           } else if (t + 1 < R) {
             issue_round(roff_next, nxt, 0);
           }
@@ -728,48 +764,49 @@ int env_i(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int LPW, int MINB, int ISO, int NBUF>
+template <int LPW, int MINB, int ISO, int NBUF, bool F32>
 void launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
-  const size_t smem = 64 + (size_t)G * 48 * d.n + (size_t)NBUF * (HDRB + 32 * BLKB) + (NBUF == 2 ? 16 : 0);   // NBUF 1, 64 bodies: 20096 B, 11 CTAs per SM
-  cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = 64 + (size_t)G * 48 * d.n + (size_t)NBUF * (HDRB + 32 * ((F32 ? RECB32 : RECB64) + LAMB)) + (NBUF == 2 ? 16 : 0);   // NBUF 1, 64 bodies: 20096 B, 11 CTAs per SM
+  cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF>, 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF, F32>, 32, smem);
   if (per_sm < 1) per_sm = 1;
   const int cap = env_i("EGG_PGS_CTAS_PER_SM", 0);
   if (cap > 0 && cap < per_sm) per_sm = cap;
   const int groups = (d.W + G - 1) / G;
   const int grid = groups < sms * per_sm ? groups : sms * per_sm;
   cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
-  egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3), env_i("EGG_PGS_PFMODE", 0));
+  egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF, F32><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3), env_i("EGG_PGS_PFMODE", 0));
 }
 
 // Registers are allocated per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler
 // = 168 registers.
-template <int MINB, int ISO, int NBUF>
+template <int MINB, int ISO, bool F32>
 void launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
   switch (d.lpw) {
-    case 1: launch<1, MINB, ISO, NBUF>(d, dt, s); break;
-    case 2: launch<2, MINB, ISO, NBUF>(d, dt, s); break;
-    case 4: launch<4, MINB, ISO, NBUF>(d, dt, s); break;
-    case 16: launch<16, MINB, ISO, NBUF>(d, dt, s); break;
-    default: launch<8, MINB, ISO, NBUF>(d, dt, s); break;
+    case 1: launch<1, MINB, ISO, 1, F32>(d, dt, s); break;
+    case 2: launch<2, MINB, ISO, 1, F32>(d, dt, s); break;
+    case 4: launch<4, MINB, ISO, 1, F32>(d, dt, s); break;
+    case 16: launch<16, MINB, ISO, 1, F32>(d, dt, s); break;
+    default: launch<8, MINB, ISO, 1, F32>(d, dt, s); break;
   }
 }
+// One staging buffer (NBUF = 1).  A second buffer (two rounds in flight; the NBUF == 2 paths of the
+// kernel) was measured no better anywhere -- stack10 4096 worlds 26.9 vs 26.2 ms, legged20 106 vs
+// 90 ms, pile64 8.8 vs 8.1 ms -- and is not instantiated.
 template <int MINB, int ISO>
 void launch_nbuf(const EggDev& d, double dt, cudaStream_t s) {
-  // EGG_PGS_NBUF=2 keeps two rounds in flight.  Measured no better anywhere (stack10 4096 worlds
-  // 26.9 vs 26.2 ms, legged20 106 vs 90 ms, pile64 8.8 vs 8.1 ms): the stage copy is not what
-  // bounds narrow worlds, the ~300-instruction dependent stage is.  One buffer is the default.
-  const int nbuf = env_i("EGG_PGS_NBUF", 1);
-  if (nbuf == 2) launch_lpw<MINB, ISO, 2>(d, dt, s);
-  else launch_lpw<MINB, ISO, 1>(d, dt, s);
+  if (d.blkb == RECB32 + LAMB) launch_lpw<MINB, ISO, true>(d, dt, s);
+  else launch_lpw<MINB, ISO, false>(d, dt, s);
 }
 
 }  // namespace
+
+int egg_stream_blkb(int precision) { return (precision == 32 ? RECB32 : RECB64) + LAMB; }
 
 size_t egg_stream_rec_bytes(int W, int nrec, int lpw) {
   const int G = 32 / lpw;

@@ -78,7 +78,11 @@ typedef struct egg_desc {
   int n_bodies;     /* bodies per world (Ensemble::n_, ensembles.h:75) */
   int n_joints;     /* ball-and-socket joints per world (ensembles.h:81) */
   int max_contacts; /* per-world contact capacity after de-duplication; 0 = automatic */
-  int precision;    /* 64 (FP64, reference arithmetic); 32 is reserved */
+  int precision;    /* 64 (FP64, reference arithmetic).  32 (opt-in, PGS solver only): the constraint records of
+                       the solve are stored in FP32 (40 % fewer bytes in an HBM-bound kernel); narrowphase,
+                       assembly arithmetic, multipliers, accumulators and the integrator stay FP64, so
+                       the discrete outputs of the narrowphase are unchanged and the state agrees with
+                       the FP64 path to ~1e-6 relative per step (tested at 1e-4) */
   int solver;       /* egg_solver */
   int k_max;        /* kNumIterations = 500 */
   double tol;       /* kAllowNumericalError = 1e-9 */

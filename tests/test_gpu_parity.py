@@ -267,6 +267,35 @@ def test_full_size_pgs_runs_clean(name, W, k_max, steps):
     b.close()
 
 
+@pytest.mark.parametrize("name,W,k_max,steps", [("pile64", 4, 50, 2), ("stack10", 8, 200, 3), ("legged20", 4, 100, 3)])
+def test_pgs_fp32_records_opt_in(name, W, k_max, steps):
+    """precision = 32 (opt-in): constraint records of the solve stored in FP32, everything else FP64.
+    Stepwise from shared state against the FP64 oracle: the narrowphase outputs stay bit-exact,
+    state within 1e-4 relative (north_star's FP32 tolerance; measured ~1e-6), same sweep counts."""
+    import eggshell_b200 as E
+    scene = getattr(E.scenes, name)(W)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, taps=True, precision=32)
+    ows = [oracle_world(scene, wi, solver=1, k_max=k_max)[0] for wi in range(W)]
+    worst_all = {}
+    for s in range(steps):
+        p, R, v, w = b.bodies()
+        for k in range(W):
+            ows[k].set_state(p[k], R[k], v[k], w[k])
+        b.step(scene["dt"])
+        for ow in ows:
+            ow.step(scene["dt"])
+        worst = compare_step(b, ows, list(range(W)), tol=1e-4, check_lambda=False)
+        st = b.status()
+        assert int(st["status"].max()) == 0
+        for k in range(W):
+            assert st["sweeps"][k] == ows[k].stats()["sweeps"]
+        for key, val in worst.items():
+            worst_all[key] = max(worst_all.get(key, 0.0), val)
+    b.close()
+    print(name, "fp32 records worst", worst_all)
+    assert worst_all["v"] < 1e-4 and worst_all["w"] < 1e-4
+
+
 @pytest.mark.parametrize("name,W,k_max,lpw", [("stack10", 65536, 10, "1"), ("stack10", 65536, 10, ""), ("pile64", 16384, 5, ""), ("pile64", 8192, 5, "16"), ("legged20", 131072, 10, "")])
 def test_full_size_step_is_bit_reproducible(name, W, k_max, lpw, monkeypatch):
     """The kernels are deterministic, so the same full-size step from the same state must give the
