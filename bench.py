@@ -132,7 +132,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -357,13 +357,32 @@ def run_ours(args):
                     "steps": args.e2e_steps, "api": "egg_set_state + egg_step + egg_get_bodies (pinned host buffers)"},
             "gpu_launches": int(launches),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     b.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of rank 0, written to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries print to stdout on their own (torch's "NCCL version ..." banner at communicator
+    # creation, for one): everything written to fd 1 from here on goes to stderr, and only emit()
+    # writes to the original stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
