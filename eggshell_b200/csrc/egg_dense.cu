@@ -169,11 +169,14 @@ __device__ bool well_conditioned(double* M, int ld, int k) {
       for (int i = tid; i < k; i += DT) { double t = M[(size_t)i * ld + kk]; M[(size_t)i * ld + kk] = M[(size_t)i * ld + big]; M[(size_t)i * ld + big] = t; }
       __syncthreads();
     }
-    const double d = M[(size_t)kk * ld + kk];
-    const int rs = k - kk - 1;
-    for (int e = tid; e < rs * rs; e += DT) {
-      const int i = kk + 1 + e / rs, j = kk + 1 + e % rs;
-      M[(size_t)i * ld + j] -= M[(size_t)i * ld + kk] * M[(size_t)kk * ld + j] / d;
+    // trailing update, one column j per thread (coalesced across the threads, the multiplier
+    // column M[i][kk] is a broadcast): no integer or floating-point division in the k^3/3 loop.
+    // Only the pivot RANGE of this factorisation is used (a yes/no decision), so the rounding of
+    // a * b / d versus a * (b / d) is immaterial.
+    const double invd = 1.0 / M[(size_t)kk * ld + kk];
+    for (int j = kk + 1 + tid; j < k; j += DT) {
+      const double ukj = M[(size_t)kk * ld + j] * invd;
+      for (int i = kk + 1; i < k; i++) M[(size_t)i * ld + j] -= M[(size_t)i * ld + kk] * ukj;
     }
     __syncthreads();
   }
