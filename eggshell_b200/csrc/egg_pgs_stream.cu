@@ -11,9 +11,11 @@
 // Hence this layout: the G = 32/LPW worlds that share a warp are interleaved in memory round by
 // round ("group stream"), so that ONE bulk copy of ~4 KB feeds a whole warp-stage.
 //
-//   group stream = for round t = 0..R-1:  [48-byte header][records of world 0 in stage t]...[world G-1]
-//   header: u8 start[s] (record index of world s inside the round, start[G] = total), byte 40 =
-//   total of the next round (cyclic), so the size of the next copy is known one round ahead.
+//   group stream = for round t = 0..R-1:
+//       [64-byte header][32-byte multiplier sector of every block of the round][records of world 0's
+//       stage t]...[records of world G-1's stage t]            (padded to a multiple of 32 B)
+//   header: u8 start[s] (block index of world s inside the round, start[G] = total), bytes 40 / 41 =
+//   totals of the next two rounds (cyclic), so the size of the next copy is known one round ahead.
 //
 // Algorithm (unchanged in exact arithmetic, reference row order inside every world):
 //   * No frozen accumulator.  The reference evaluates the residual of x_k after every sweep only to
@@ -26,10 +28,13 @@
 //     (one read-only pass) and the reference's decision is taken on it; the probe then moves to
 //     the chunk that contributed most.  Sweep counts, final multipliers and the reported
 //     residual are those of the reference algorithm.
-//   * The multipliers live inside the record (REC_DDIAG slot; the row update is written in
-//     increment form  x' = x + (rhs - J a - cfm x) / (D + cfm),  so only 1/(D+cfm) is needed),
-//     are staged with it and written back in place; the read-only pass that ends a world's solve
-//     also writes them out in reference row order (lam_out / row_state taps).
+//   * The row update is written in increment form  x' = x + (rhs - J a - cfm x) / (D + cfm),  so
+//     only 1/(D+cfm) is stored.  The multipliers are staged with their round (one 32-byte sector
+//     per block, contiguous per round) and written back in place with full-sector stores; the
+//     read-only pass that ends a world's solve also writes them out in reference row order
+//     (lam_out / row_state taps).
+//   * Ordering between this warp's shared-memory loads of a stage and the TMA copy of the next
+//     one is a cross-proxy fence (fence.proxy.async.shared::cta), see the comment at the fence.
 //   * World groups are handed out by an atomic counter.
 //
 // Per warp: 64 B + G x n x 48 B accumulators + 64 B + G x LPW x 240 B staging.  64-body worlds:
