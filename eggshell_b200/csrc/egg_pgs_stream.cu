@@ -83,9 +83,6 @@ __device__ __forceinline__ unsigned long long policy_evict_first() {
   return p;
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ unsigned long long policy_evict_last() {
   unsigned long long p;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
@@ -153,7 +150,7 @@ __device__ __forceinline__ void st_sector(double* p, double a, double b, double 
 constexpr int HDRB = 64;      // round header bytes (keeps the multiplier sectors 32-byte aligned)
 // bytes of a round with `total` blocks: header, multipliers, records, padded to a sector
 __host__ __device__ inline unsigned round_bytes(int total, int blkb) { return (unsigned)(HDRB + blkb * total + 31) & ~31u; }
-constexpr int HDR_NEXT = 40;  // bytes 40, 41: total blocks of the next round and of the one after (cyclic)
+constexpr int HDR_NEXT = 40;  // byte 40: total blocks of the next round (cyclic); byte 41: of the one after (unused)
 
 __host__ __device__ inline size_t group_stride_bytes(int nrec, int G) { return ((size_t)nrec * ((size_t)BLKB_MAX * G + HDRB + 32) + 255) & ~(size_t)255; }
 
@@ -338,10 +335,8 @@ enum { PH_INIT = 0, PH_PROBE = 1, PH_EXACT = 2, PH_UPDATE = 3 };
 // inverse inertias, see egg_solve.cu) and comes as one 16-byte load per body.  ISO == 2: all
 // bodies of the batch share the same (1/m, 1/c) (every body of the reference is the same cube,
 // body.h:91) and the pair is a kernel constant.
-// NBUF: staging buffers = rounds in flight (2 where shared memory allows: a stage's copy has ~1 us
-// of latency even from L2, narrow worlds are bound by exactly that round trip).
-template <int LPW, int MINB, int ISO, int NBUF, bool F32>
-__global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt, int pf, int pfmode) {
+template <int LPW, int MINB, int ISO, bool F32>
+__global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, double dt, int pf) {
   constexpr int G = 32 / LPW;
   constexpr int RECB = F32 ? RECB32 : RECB64;   // bytes of one staged record
   constexpr int SPIECES = RECB / 16;
@@ -356,19 +351,17 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
   constexpr int STG = HDRB + 32 * BLKB;        // one staging buffer: header + 32 blocks
   unsigned char* stage0 = smraw + 64 + (size_t)G * 48 * n;
   const unsigned stage_s = s32(stage0);
-  const unsigned bar_b1 = s32(stage0 + NBUF * STG);   // round barrier of buffer 1 (NBUF == 2), behind the staging buffers
   const double cfm = d.prm.cfm;
   const int nj = d.nj;
   const unsigned FULL = 0xffffffffu;
 
   if (lane == 0) {
     mbar_init(bar, 1);
-    if (NBUF == 2) mbar_init(bar_b1, 1);
     mbar_init(bar2, G);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (lane < 6) reinterpret_cast<double*>(smraw + 16)[lane] = 0.0;
-  const unsigned long long pol = (pfmode & 2) ? policy_evict_last() : policy_evict_first();
+  const unsigned long long pol = policy_evict_first();
   const unsigned long long pol_keep = policy_evict_last();
   double um = 0.0, uc = 0.0;                   // ISO == 2: the batch-wide (1/m, 1/c)
   if (ISO == 2) { um = d.minv_iso[0]; uc = d.minv_iso[1]; }
@@ -407,19 +400,14 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
     unsigned best_off = 0;
     int best_meta = 0;
 
-    auto issue_round = [&](unsigned off, int total, int b) {   // one bulk copy feeds the whole warp-stage
+    auto issue_round = [&](unsigned off, int total) {          // one bulk copy feeds the whole warp-stage
       if (lane == 0) {
         const unsigned bytes = round_bytes(total, BLKB);
-        const unsigned br = (NBUF == 2 && b) ? bar_b1 : bar;
-        mbar_arrive_tx(br, bytes);
-        bulk_g2s(stage_s + (NBUF == 2 ? b * STG : 0), gs + off, bytes, br, pol);
+        mbar_arrive_tx(bar, bytes);
+        bulk_g2s(stage_s, gs + off, bytes, bar, pol);
       }
     };
-    const int tot1 = d.grp_info[(size_t)grp * 4 + 3];         // blocks in round 1 (= round 0 when R == 1)
-    auto start_rounds = [&]() {                               // the first NBUF rounds of a pass
-      issue_round(0, tot0, 0);
-      if (NBUF == 2 && R > 1) issue_round(round_bytes(tot0, BLKB), tot1, 1);
-    };
+    auto start_rounds = [&]() { issue_round(0, tot0); };      // round 0 of a pass
     auto issue_probe = [&](bool on) {                       // every world leader arrives exactly once
       if (sl == 0) {
         if (on && probe_cnt > 0) {
@@ -577,7 +565,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         unsigned roff = 0;
         double2 buf[SPIECES];
         for (int t = 0; t < nsteps; t++) {
-          int start, total = 0, nxt = 0, nxt2 = 0, cnt;
+          int start, total = 0, nxt = 0, cnt;
           const unsigned char* stage = stage0;
           if (probe) {                             // the world's own chunk, in its slice of the staging buffer
             mbar_wait(bar2, parity2);
@@ -585,15 +573,13 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
             start = sub * LPW;
             cnt = probe_cnt;
           } else {
-            const int b = (NBUF == 2) ? (t & 1) : 0;
-            stage = stage0 + b * STG;
-            mbar_wait(b ? bar_b1 : bar, (parity >> b) & 1u);
-            parity ^= 1u << b;
-            start = stage[sub]; total = stage[G]; nxt = stage[HDR_NEXT]; nxt2 = stage[HDR_NEXT + 1];
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+            start = stage[sub]; total = stage[G]; nxt = stage[HDR_NEXT];
             cnt = (int)stage[sub + 1] - start;
-            if (total > 32 || nxt > 32 || nxt2 > 32 || cnt < 0 || cnt > LPW || start + cnt > total) {   // same guard for the header
+            if (total > 32 || nxt > 32 || cnt < 0 || cnt > LPW || start + cnt > total) {   // same guard for the header
               if (sl == 0 && valid) atomicOr(&d.status[wc], 64);
-              cnt = 0; total = min(total, 32); nxt = min(nxt, 32); nxt2 = min(nxt2, 32);
+              cnt = 0; total = min(total, 32); nxt = min(nxt, 32);
             }
           }
           const bool mine = on && sl < cnt;
@@ -622,10 +608,8 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           const unsigned roff_next = roff + round_bytes(total, BLKB);
           if (probe) {
             start_rounds();                        // speculate "continue": the first rounds stream in meanwhile
-          } else if (NBUF == 2) {
-            if (t + 2 < R) issue_round(roff_next + round_bytes(nxt, BLKB), nxt2, t & 1);
           } else if (t + 1 < R) {
-            issue_round(roff_next, nxt, 0);
+            issue_round(roff_next, nxt);
           }
           if (!probe && pf > 0) {
             // HBM -> L2 prefetch cursor kept pf x 4 KB ahead of the consumer (one 128-byte line per
@@ -637,12 +621,8 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
 #pragma unroll
             for (int q = 0; q < 2; q++) {
               if (lead < pf * 4096) {
-                if (!(pfmode & 1)) {
-                  const unsigned a = pf_pos + lane * 128;
-                  if (a < stream_bytes) prefetch_l2(gs + a);
-                } else if ((pfmode & 1) && lane == 0) {
-                  bulk_prefetch_l2(gs + pf_pos, min(4096u, stream_bytes - pf_pos));
-                }
+                const unsigned a = pf_pos + lane * 128;
+                if (a < stream_bytes) prefetch_l2(gs + a);
                 pf_pos += 4096;
                 lead += 4096;
                 if (pf_pos >= stream_bytes) pf_pos = 0;
@@ -691,8 +671,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         if (phase == PH_UPDATE) {
           // multipliers were written with generic stores; the async proxy reads them back next sweep
           // (.global: the multipliers live in global memory; the space-less form also emits MEMBAR.ALL.GPU)
-          if (pfmode & 16) asm volatile("fence.proxy.async;" ::: "memory");
-          else asm volatile("fence.proxy.async.global;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
           __syncwarp();
           ++k;
         }
@@ -769,23 +748,23 @@ int env_i(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int LPW, int MINB, int ISO, int NBUF, bool F32>
+template <int LPW, int MINB, int ISO, bool F32>
 void launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
-  const size_t smem = 64 + (size_t)G * 48 * d.n + (size_t)NBUF * (HDRB + 32 * ((F32 ? RECB32 : RECB64) + LAMB)) + (NBUF == 2 ? 16 : 0);   // NBUF 1, 64 bodies: 20096 B, 11 CTAs per SM
-  cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = 64 + (size_t)G * 48 * d.n + (size_t)(HDRB + 32 * ((F32 ? RECB32 : RECB64) + LAMB));   // FP64, 64 bodies: 20096 B, 11 CTAs per SM
+  cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF, F32>, 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO, F32>, 32, smem);
   if (per_sm < 1) per_sm = 1;
   const int cap = env_i("EGG_PGS_CTAS_PER_SM", 0);
   if (cap > 0 && cap < per_sm) per_sm = cap;
   const int groups = (d.W + G - 1) / G;
   const int grid = groups < sms * per_sm ? groups : sms * per_sm;
   cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
-  egg_pgs_stream_kernel<LPW, MINB, ISO, NBUF, F32><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3), env_i("EGG_PGS_PFMODE", 0));
+  egg_pgs_stream_kernel<LPW, MINB, ISO, F32><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3));
 }
 
 // Registers are allocated per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler
@@ -793,16 +772,16 @@ void launch(const EggDev& d, double dt, cudaStream_t s) {
 template <int MINB, int ISO, bool F32>
 void launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
   switch (d.lpw) {
-    case 1: launch<1, MINB, ISO, 1, F32>(d, dt, s); break;
-    case 2: launch<2, MINB, ISO, 1, F32>(d, dt, s); break;
-    case 4: launch<4, MINB, ISO, 1, F32>(d, dt, s); break;
-    case 16: launch<16, MINB, ISO, 1, F32>(d, dt, s); break;
-    default: launch<8, MINB, ISO, 1, F32>(d, dt, s); break;
+    case 1: launch<1, MINB, ISO, F32>(d, dt, s); break;
+    case 2: launch<2, MINB, ISO, F32>(d, dt, s); break;
+    case 4: launch<4, MINB, ISO, F32>(d, dt, s); break;
+    case 16: launch<16, MINB, ISO, F32>(d, dt, s); break;
+    default: launch<8, MINB, ISO, F32>(d, dt, s); break;
   }
 }
-// One staging buffer (NBUF = 1).  A second buffer (two rounds in flight; the NBUF == 2 paths of the
-// kernel) was measured no better anywhere -- stack10 4096 worlds 26.9 vs 26.2 ms, legged20 106 vs
-// 90 ms, pile64 8.8 vs 8.1 ms -- and is not instantiated.
+// One staging buffer per warp.  A second buffer (two rounds in flight) was measured no better
+// anywhere -- stack10 4096 worlds 26.9 vs 26.2 ms, legged20 106 vs 90 ms, pile64 8.8 vs 8.1 ms --
+// and was removed again.
 template <int MINB, int ISO>
 void launch_nbuf(const EggDev& d, double dt, cudaStream_t s) {
   if (d.blkb == RECB32 + LAMB) launch_lpw<MINB, ISO, true>(d, dt, s);
