@@ -137,7 +137,7 @@ int egg_stage_cap(const EggDev& d) {
     // -- unless the batch is too small to give every SM a few warps that way
     if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16) {
       lpw = (d.n <= 12) ? 1 : (d.n <= 24 ? 4 : 8);
-      const long long want = (long long)num_sms() * env_int("EGG_PGS_MIN_WARPS_PER_SM", 4);
+      const long long want = (long long)num_sms() * env_int("EGG_PGS_MIN_WARPS_PER_SM", 3);
       while (lpw < 8 && (long long)d.W * lpw / 32 < want) lpw *= 2;
     }
     return lpw;
