@@ -31,6 +31,10 @@ WORKLOADS = {
     # name: (scene fn name, kwargs, default worlds per GPU, description)
     "c2": ("stack10", {}, 4096, "4096 worlds x 10-box stack on ground plane, contact-only PGS"),
     "c3": ("pile64", {}, 65536, "65536 worlds x 64-body random box pile, contact-rich PGS"),
+    # BASELINE.json configs[3]: the dense Schur + Murty solve of lcp.cc.  The timed state is the scene
+    # after SETTLE["c4"] steps: the chain has landed and rests on ~47 ground contacts (~240 rows,
+    # 96 of them equality rows), ~180 Murty pivots per step.
+    "c4": ("chain32", {}, 16384, "16384 worlds x 32-link articulated chain (ball joints + ground contact), dense Schur + Murty LCP"),
     "c5": ("legged20", {}, 131072, "worlds x 20-body legged ensemble (19 ball joints + foot contacts), PGS"),
     # MPC rollout sweep (BASELINE.json configs[4]): a timed "step" = one 50-step horizon from the
     # common start state (egg_restore + 50 x egg_step, state evolving inside the horizon) followed
@@ -38,6 +42,9 @@ WORKLOADS = {
     "c5mpc": ("legged20", {}, 131072, "MPC rollout sweep: worlds x 20-body legged ensemble, 50-step horizons, cost allgather"),
 }
 HORIZON = {"c5mpc": 50}
+SETTLE = {"c4": 4}            # steps taken from the scene's start state before the snapshot that every timed step restores
+DENSE = {"c4"}                # workloads on the reference's default dense solver (solver 0); the others use PGS (solver 1)
+FIXED_K = 20
 FLOPS_PER_ROW_UPDATE = 54.0
 ROW_STREAM_BYTES = 240.0      # one row streamed from HBM
 
@@ -54,6 +61,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fixed-k", action="store_true", help="skip the extra fixed-K (K = 20) measurement of the c3 workload")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="32 = opt-in FP32 constraint records (not the headline)")
     return ap.parse_args()
 
@@ -69,7 +77,7 @@ def peaks():
 def scene_for(args, W, rank):
     import eggshell_b200 as E
     fn, kw, _, _ = WORKLOADS[args.workload]
-    base = {"stack10": 1000, "pile64": 3000, "legged20": 5000}[fn]
+    base = {"stack10": 1000, "pile64": 3000, "legged20": 5000, "chain32": 4000}[fn]
     return getattr(E.scenes, fn)(W, seed=[base, rank], **kw)
 
 
@@ -81,9 +89,13 @@ def cpu_reference(args, cores, seconds, steps_per_sample=1):
     from oracle import pyoracle as O
     from tests.helpers import oracle_world
     fn, kw, _, _ = WORKLOADS[args.workload]
+    solver = 0 if args.workload in DENSE else 1
+    settle = SETTLE.get(args.workload, 0)
     # calibrate with one world-step on one thread
     sc = scene_for(args, 1, 0)
-    w0, _ = oracle_world(sc, 0, solver=1, k_max=args.k_max)
+    w0, _ = oracle_world(sc, 0, solver=solver, k_max=args.k_max)
+    for _ in range(settle):
+        w0.step(sc["dt"])
     t0 = time.perf_counter()
     w0.step(sc["dt"])
     t1 = time.perf_counter() - t0
@@ -91,12 +103,14 @@ def cpu_reference(args, cores, seconds, steps_per_sample=1):
     per_core = min(per_core, 4096)
     nw = per_core * cores
     sc = scene_for(args, nw, 0)
-    worlds = [oracle_world(sc, w, solver=1, k_max=args.k_max)[0] for w in range(nw)]
+    worlds = [oracle_world(sc, w, solver=solver, k_max=args.k_max)[0] for w in range(nw)]
+    if settle:                            # untimed: bring the sample to the state the GPU arm is timed on
+        O.batch_step(worlds, sc["dt"], settle, cores)
     sec, rows_sweeps, rows = O.batch_step(worlds, sc["dt"], steps_per_sample, cores)
     ws = nw * steps_per_sample
     return dict(value=ws / sec, unit="world-steps/s", cores=cores, kind="port",
                 sample=f"{nw} worlds x {steps_per_sample} step(s) of {WORKLOADS[args.workload][3]} on {cores} host threads "
-                       f"({sec:.2f} s); oracle/ = Eigen-free restatement of the reference step, g++ -O2 -march=native",
+                       f"({sec:.2f} s{', after %d untimed settling steps' % settle if settle else ''}); oracle/ = Eigen-free restatement of the reference step, g++ -O2 -march=native",
                 rows_per_s=rows_sweeps / sec, seconds=sec, world_steps=ws)
 
 
@@ -125,8 +139,8 @@ def run_reference(args):
         "impl": "reference", "metric": "world-steps/sec", "value": value, "unit": "world-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "solver": "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01,
-                   "dt": 0.005, "inputs": "bounded CPU sample of the same workload per step"},
+        "config": {"workload": f"{args.workload}: {desc}", "solver": "dense-murty" if args.workload in DENSE else "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01,
+                   "inputs": "bounded CPU sample of the same workload per step (same scene, same solver, same termination; fewer worlds)"},
         "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": cores, "kind": "port", "sample": res["sample"]},
         "pgs_rows_per_s": rps / sec,
         "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -208,7 +222,9 @@ def run_ours(args):
     n, nj, dt = scene["n"], scene["nj"], scene["dt"]
     maxc = {"c3": 1024}.get(args.workload, 0)
     horizon = HORIZON.get(args.workload, 1)
-    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=args.k_max, max_contacts=maxc, device=local, precision=args.precision)
+    dense = args.workload in DENSE
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_DENSE_MURTY if dense else E.SOLVER_PGS, k_max=args.k_max, max_contacts=maxc,
+                            device=local, precision=args.precision)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
     costs = torch.zeros(W, dtype=torch.float64, device="cuda")
@@ -221,6 +237,9 @@ def run_ours(args):
 
     # Every step starts from the named scene's state (device-resident snapshot), so all K steps
     # do the same work: step = egg_restore (D2D, inside the timed region) + egg_step.
+    settle = SETTLE.get(args.workload, 0)
+    if settle:
+        b.step(dt, n_steps=settle)
     b.snapshot()
     # ---- warm-up ----
     for _ in range(max(args.warmup, 0)):
@@ -273,8 +292,8 @@ def run_ours(args):
     # inputs = the scene's initial state in pinned host memory; outputs land in a second pinned set
     hin = (E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3, 3)), E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3)))
     hout = (E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3, 3)), E.pinned_empty((W, n, 3)), E.pinned_empty((W, n, 3)))
-    for dst, src in zip(hin, (scene["p"], scene["R"], scene["v"], scene["w"])):
-        dst[...] = src
+    b.restore()
+    b.bodies(out=hin)                    # the timed state (= the scene's start state unless the workload settles first)
     h2d = d2h = sum(x.nbytes for x in hin)
     for _ in range(1):
         b.set_state(*hin); b.step(dt, n_steps=horizon); b.bodies(out=hout)
@@ -291,6 +310,38 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = W * world * args.e2e_steps * horizon / (float(t2.item()) * 1e-3)
+
+    dense_flops = float(b.dense_work().sum()) if dense else None
+
+    # ---- fixed-K line (reference termination AND fixed-K throughput): the same workload
+    # with the sweep count pinned to K = 20; parity at the same K: test_pgs_fixed_k20_stepwise ----
+    fixed_k = None
+    if args.workload == "c3" and args.k_max != FIXED_K and not args.no_fixed_k:
+        b.close()
+        b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=FIXED_K, max_contacts=maxc, device=local, precision=args.precision)
+        b.set_stream(stream.cuda_stream)
+        b.snapshot()
+        for _ in range(3):
+            b.restore(); b.step(dt)
+        b.sync()
+        b.set_profiling(True); b.kernel_ms()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            b.restore(); b.step(dt)
+        g1.record(stream)
+        barrier()
+        t3 = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        k3 = b.kernel_ms()
+        b.set_profiling(False)
+        st3 = b.status()
+        fixed_k = {"k": FIXED_K, "value": W * world * args.steps / (float(t3.item()) * 1e-3), "unit": "world-steps/s",
+                   "ms_per_step": float(t3.item()) / max(args.steps, 1), "mean_sweeps": float(st3["sweeps"].mean()),
+                   "kernel_ms_per_step": {"narrowphase": k3[0] / max(k3[3], 1.0), "assembly": k3[1] / max(k3[3], 1.0), "solve_integrate": k3[2] / max(k3[3], 1.0)},
+                   "status_or": int(np.bitwise_or.reduce(st3["status"])), "parity": "tests/test_gpu_parity.py::test_pgs_fixed_k20_stepwise"}
 
     if rank == 0:
         pk, pk_kind = peaks()
@@ -316,25 +367,42 @@ def run_ours(args):
             traffic = tr.get(key, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-        roof = {"bound": "hbm", "kernel": "egg_pgs_stream_kernel (PGS solve + fused integrate)", "achieved": achieved,
-                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_source": pk_kind,
-                "traffic": traffic, "kernel_ms": solve_ms, "kernel_share_of_step": kms[2] / max(kms[0] + kms[1] + kms[2], 1e-9),
-                "algorithmic_bytes_per_launch": solve_bytes,
-                "definition": "W*B_step + sum_worlds blocks*((sweeps+2)*240 + sweeps*32) bytes: every block streamed once per Gauss-Seidel pass (SURVEY 8d), multipliers written back once per sweep"}
-        # the same kernel against a single pass over the rows (records counted once per launch): what a solve
-        # with all rows resident on chip would move; kept for reference, see DESIGN.md section 3
-        once_bytes = W * (bytes_step + 3.0 * nc_mean * ROW_STREAM_BYTES)
-        roof_once = {"bound": "hbm", "achieved": once_bytes / (solve_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": once_bytes / (solve_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_launch": once_bytes}
+        # two bounds for the dominant kernel, the larger fraction is the roofline.
+        #   HBM : algorithmic bytes = W x B_step (state in/out, static data, joints, cost) per launch
+        #   FP64: algorithmic flops = 54 per PGS row update x rows x sweeps (both counted by the kernel)
+        # against the measured copy bandwidth (MEASURED_PEAKS.json) and a DFMA microbenchmark of this
+        # run.  The kernel's own record stream (rows re-read every sweep) is NOT algorithmic traffic:
+        # it is reported separately as roofline_stream / wasted_traffic.
         try:
             fp64_peak = E.batch.fp64_peak_tflops(local)
         except Exception:
             fp64_peak = None
-        flops = FLOPS_PER_ROW_UPDATE * sweeps_last
-        roof64 = {"bound": "fp64", "achieved": flops / (solve_ms * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                  "frac": (flops / (solve_ms * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                  "peak_source": "DFMA microbenchmark (egg_fp64_peak_tflops), this run",
-                  "flops_per_row_update": FLOPS_PER_ROW_UPDATE}
+        flops = dense_flops if dense else FLOPS_PER_ROW_UPDATE * sweeps_last
+        algo_bytes = float(W * bytes_step)
+        hbm_ach = algo_bytes / (solve_ms * 1e-3) / 1e9
+        f64_ach = flops / (solve_ms * 1e-3) / 1e12
+        hbm_frac = hbm_ach / pk["hbm_gbs"]
+        f64_frac = (f64_ach / fp64_peak) if fp64_peak else None
+        share = kms[2] / max(kms[0] + kms[1] + kms[2], 1e-9)
+        kname = "egg_dense_kernel (cfm decision + Schur + Murty + fused integrate)" if dense else "egg_pgs_stream_kernel (PGS solve + fused integrate)"
+        roof_hbm = {"bound": "hbm", "kernel": kname, "achieved": hbm_ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if pk_kind == "measured" else "fallback 6650 GB/s (MEASURED_PEAKS.json absent)",
+                    "algorithmic_bytes_per_launch": algo_bytes, "definition": "W x B_step, B_step = n(2*144+128) + 56 nj + 8 (SURVEY 8d)"}
+        roof_f64 = {"bound": "fp64", "kernel": kname, "achieved": f64_ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": f64_frac,
+                    "peak_source": "DFMA microbenchmark of this run (egg_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
+                    "algorithmic_flops_per_launch": flops,
+                    "definition": ("operations of the reference algorithm counted by the kernel per world (egg_get_dense_work): cfm-decision factorisation R^3/3, "
+                                   "A_ee^-1 2E^3, Schur products, and per Murty pivot LDL^T k^3/3 + solves 2k^2 + w 2k(I-k)") if dense else
+                                  "54 flop x rows x sweeps (SURVEY 8d), rows and sweeps counted by the kernel"}
+        roof = dict(roof_f64 if (f64_frac is not None and f64_frac >= hbm_frac) else roof_hbm)
+        roof.update({"traffic": traffic, "kernel_ms": solve_ms, "kernel_share_of_step": share})
+        if traffic:
+            roof["wasted_traffic"] = traffic / algo_bytes
+        roof_other = roof_hbm if roof["bound"] == "fp64" else roof_f64
+        # efficiency of the kernel on the traffic it chose to generate (every block streamed once per pass)
+        roof_stream = None if dense else {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                       "stream_bytes_per_launch": solve_bytes, "stream_over_algorithmic": solve_bytes / algo_bytes,
+                       "definition": "NOT the roofline: DRAM efficiency on the kernel's own record stream, W*B_step + sum_worlds blocks*((sweeps+2)*240 + sweeps*32) bytes"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as O
@@ -345,18 +413,22 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_max / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if args.precision == 64 else "f64 arithmetic, f32 constraint records", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "worlds_per_gpu": W, "bodies": n, "joints": nj,
-                       "solver": "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01, "dt": dt, "horizon": horizon, "parallelism": f"worlds sharded x{world}",
-                       "step": "every timed step = egg_restore(scene state, D2D) + egg_step: all steps do the same work",
+                       "solver": "dense-murty" if dense else "pgs", "k_max": args.k_max, "tol": 1e-9, "cfm": 0.01, "dt": dt, "horizon": horizon, "parallelism": f"worlds sharded x{world}",
+                       "step": "every timed step = egg_restore(timed state, D2D) + egg_step: all steps do the same work",
+                       "timed_state": ("scene after %d settling steps" % settle) if settle else "the scene's start state",
+                       "mean_pivots": float(st["pivots"].mean()) if dense else None,
                        "l2": "inputs larger than L2 (state %.0f MB + rows %.0f MB per rank)" % (W * n * 34 * 8 / 1e6, W * nc_mean * 256 / 1e6),
                        "mean_contacts_per_world": contacts_mean, "mean_rows_per_world": rows_last / W,
                        "mean_sweeps": sweeps_last / max(rows_last, 1.0), "status_or": status_or, "best_cost": best},
             "pgs_rows_per_s": sweeps_last / (solve_ms * 1e-3),
             "kernel_ms_per_step": {"narrowphase": kms[0] / steps_counted, "assembly": kms[1] / steps_counted, "solve_integrate": solve_ms},
-            "roofline": roof, "roofline_rows_once": roof_once, "roofline_fp64": roof64, "cpu_baseline": cpu, "clocks": clocks,
+            "roofline": roof, "roofline_other_bound": roof_other, "roofline_stream": roof_stream, "cpu_baseline": cpu, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": args.e2e_steps, "api": "egg_set_state + egg_step + egg_get_bodies (pinned host buffers)"},
             "gpu_launches": int(launches),
         }
+        if fixed_k is not None:
+            line["fixed_k"] = fixed_k
         emit(line)
     b.close()
     if world > 1:

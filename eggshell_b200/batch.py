@@ -22,8 +22,8 @@ ST_LCP_FAILED, ST_JOINT_CONFLICT, ST_BAD_INIT, ST_CONTACT_OVERFLOW, ST_NONFINITE
 
 EXPORTS = [
     "egg_desc_default", "egg_create", "egg_destroy", "egg_set_bodies", "egg_set_state", "egg_set_joints",
-    "egg_set_external", "egg_init", "egg_init_stabilize", "egg_step", "egg_snapshot", "egg_restore", "egg_update_contacts", "egg_get_static", "egg_get_bodies", "egg_get_contacts", "egg_get_pair_hits",
-    "egg_get_status", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
+    "egg_set_external", "egg_init", "egg_init_stabilize", "egg_post_stabilize", "egg_step", "egg_snapshot", "egg_restore", "egg_update_contacts", "egg_get_static", "egg_get_bodies", "egg_get_contacts", "egg_get_contacts_range", "egg_get_pair_hits", "egg_get_pair_hits_range",
+    "egg_get_status", "egg_get_dense_work", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
     "egg_launch_count", "egg_capacity", "egg_set_profiling", "egg_get_kernel_ms", "egg_fp64_peak_tflops", "egg_host_alloc", "egg_host_free", "egg_last_error", "egg_version",
 ]
 
@@ -166,6 +166,13 @@ class Batch:
         _chk(lib().egg_init_stabilize(self.h, int(max_steps), _p(steps), _p(e2)), "egg_init_stabilize")
         return steps, e2
 
+    def post_stabilize(self, max_steps=500):
+        """Ensemble::PostStabilize; returns (stabilisation steps taken [W], final squared error [W])."""
+        steps = np.zeros(self.W, dtype=np.int32)
+        e2 = np.zeros(self.W)
+        _chk(lib().egg_post_stabilize(self.h, int(max_steps), _p(steps), _p(e2)), "egg_post_stabilize")
+        return steps, e2
+
     def set_stream(self, cuda_stream_ptr):
         _chk(lib().egg_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "egg_set_stream")
 
@@ -200,15 +207,17 @@ class Batch:
         _chk(lib().egg_get_bodies(self.h, _p(p), _p(R), _p(v), _p(w)), "egg_get_bodies")
         return p, R, v, w
 
-    def contacts(self):
-        W, mc, nr = self.W, self.max_contacts, self.nrec
+    def contacts(self, first=0, n_worlds=None):
+        """Contact taps of the last step; `first` / `n_worlds` select a world range (default: all)."""
+        W = self.W - first if n_worlds is None else n_worlds
+        mc, nr = self.max_contacts, self.nrec
         count = np.zeros(W, dtype=np.int32)
         i0, i1, code = (np.zeros((W, mc), dtype=np.int32) for _ in range(3))
         pos, nrm, depth = np.zeros((W, mc, 3)), np.zeros((W, mc, 3)), np.zeros((W, mc))
         lam = np.zeros((W, 3 * nr))
         rs = np.zeros((W, 3 * nr), dtype=np.int32)
-        _chk(lib().egg_get_contacts(self.h, _p(count), _p(i0), _p(i1), _p(pos), _p(nrm), _p(depth), _p(code),
-                                    _p(lam), _p(rs)), "egg_get_contacts")
+        _chk(lib().egg_get_contacts_range(self.h, int(first), int(W), _p(count), _p(i0), _p(i1), _p(pos), _p(nrm), _p(depth),
+                                          _p(code), _p(lam), _p(rs)), "egg_get_contacts_range")
         return dict(count=count, i0=i0, i1=i1, pos=pos, nrm=nrm, depth=depth, code=code, lam=lam, row_state=rs)
 
     def pair_hits(self):
@@ -227,6 +236,12 @@ class Batch:
         return dict(status=st, n_contacts_raw=stats[:, 0], n_contacts=stats[:, 1], n_rows=stats[:, 2],
                     n_pair_hits=stats[:, 3], sweeps=stats[:, 4], pivots=stats[:, 5], cfm_applied=stats[:, 6],
                     residual=res)
+
+    def dense_work(self):
+        """FP64 operations of the reference algorithm on each world's last dense solve [W]."""
+        out = np.zeros(self.W)
+        _chk(lib().egg_get_dense_work(self.h, _p(out)), "egg_get_dense_work")
+        return out
 
     def rollout_costs(self, device_ptr):
         _chk(lib().egg_rollout_costs(self.h, C.c_void_p(device_ptr)), "egg_rollout_costs")

@@ -17,7 +17,6 @@ UNITS = [
     ("egg_solve.cu", []),
     ("egg_pgs.cu", []),
     ("egg_iter.cu", []),
-    ("egg_pgs_fast.cu", []),
     ("egg_pgs_stream.cu", []),
     ("egg_dense.cu", ["-fmad=false"]),
     ("egg_capi.cu", []),

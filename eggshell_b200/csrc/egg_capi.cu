@@ -10,11 +10,12 @@
 #include <string>
 #include <vector>
 
-void egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes);
+cudaError_t egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes);
 size_t egg_dense_scratch_bytes(const EggDev& d);
+int egg_dense_smem_fits(const EggDev& d, size_t limit);
 double egg_measure_fp64_tflops();
-void egg_launch_relax(const EggDev& d, double dt, double step_scale, int max_steps, void* scratch, int* prog, double* err2, int* any_active,
-                      cudaStream_t s);
+cudaError_t egg_launch_relax(const EggDev& d, double dt, double step_scale, int max_steps, int mode, void* scratch, size_t scratch_bytes,
+                             int* prog, double* err2, int* any_active, cudaStream_t s);
 
 static thread_local std::string g_err;
 static void set_err(const char* what, cudaError_t e) {
@@ -27,6 +28,16 @@ static void set_err(const char* what, cudaError_t e) {
     cudaError_t e__ = (call);                   \
     if (e__ != cudaSuccess) {                   \
       set_err(#call, e__);                      \
+      return EGG_ERR_CUDA;                      \
+    }                                           \
+  } while (0)
+// CK for egg_create after the batch exists: releases it on failure
+#define CKB(call)                               \
+  do {                                          \
+    cudaError_t e__ = (call);                   \
+    if (e__ != cudaSuccess) {                   \
+      set_err(#call, e__);                      \
+      egg_destroy(b);                           \
       return EGG_ERR_CUDA;                      \
     }                                           \
   } while (0)
@@ -45,12 +56,27 @@ struct egg_batch {
   size_t stage_bytes = 0;
   void* dense_scratch = nullptr;
   size_t dense_scratch_bytes = 0;
+  int* relax_prog = nullptr;     // [2 W] relaxation progress, allocated by the first stabilisation call
+  double* relax_err2 = nullptr;  // [W]
+  int* relax_any = nullptr;      // [1]
+  double* rec_aux = nullptr;     // per-world records for the relaxation when dev.rec holds the PGS group stream
+  int* level_aux = nullptr;
   int device = 0;
   double* snap = nullptr;        // egg_snapshot copy of dev.dyn
   bool profiling = false;
   std::vector<cudaEvent_t> ev;   // 4 per profiled step
   std::vector<cudaEvent_t> ev_free;
 };
+
+// LK(wrapper call): a launch wrapper's cudaError_t -> EGG_ERR_CUDA with the wrapper named
+#define LK(call)                                \
+  do {                                          \
+    cudaError_t e__ = (call);                   \
+    if (e__ != cudaSuccess) {                   \
+      set_err(#call, e__);                      \
+      return EGG_ERR_CUDA;                      \
+    }                                           \
+  } while (0)
 
 template <class T>
 static int dalloc(egg_batch* b, T** p, size_t count) {
@@ -154,18 +180,13 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
     DA(d.pair_code, (size_t)W * d.P);
     DA(d.pair_cnt, (size_t)W * d.P);
   }
-  {
-    // record format 1 (multipliers inside the record) belongs to the default "stream" PGS variant;
-    // EGG_PGS_VARIANT=fast selects the earlier per-world-record kernel (format 0)
-    const char* pv = getenv("EGG_PGS_VARIANT");
-    d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS && (!pv || pv[0] == 's')) ? 1 : 0;
-    // the group-stream assembly keeps u16 level tables of 2 (n + 4 nrec) bytes per world in shared
-    // memory: beyond ~24 k constraint slots per world the per-world-record kernel takes over
-    if (d.nrec > 24000) d.rec_fmt = 0;
-    if (dsc->precision == 32 && !d.rec_fmt) { g_err = "precision = 32 needs the default (stream) PGS kernel"; return EGG_ERR_UNSUPPORTED; }
-  }
+  // The PGS solver streams group-interleaved records (format 1, egg_pgs_stream.cu); the dense path,
+  // Jacobi / SOR and the relaxation read per-world 240-byte records (format 0, egg_pgs.cu).
+  d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS) ? 1 : 0;
+  // the group-stream assembly keeps u16 level tables of 2 (n + 4 nrec) bytes per world in shared memory
+  if (d.rec_fmt && d.nrec > 24000) { g_err = "PGS: more than 24000 constraint slots per world (n_joints + max_contacts) are not supported"; egg_destroy(b); return EGG_ERR_UNSUPPORTED; }
   if (d.rec_fmt) {
-    // group stream of the default PGS variant: G = 32 / lpw worlds share one interleaved record stream
+    // group stream: G = 32 / lpw worlds share one interleaved record stream
     d.lpw = egg_stage_cap(d);
     d.blkb = egg_stream_blkb(dsc->precision);
     const int groups = (W + 32 / d.lpw - 1) / (32 / d.lpw);
@@ -177,13 +198,13 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   } else {
     DA(d.rec, (size_t)W * d.nrec * EGG_REC);
   }
-  DA(d.lam, (size_t)W * d.nrec * 3);
-  DA(d.lam2, (size_t)W * d.nrec * 3);
-  if (dsc->solver == EGG_SOLVER_PGS && getenv("EGG_PGS_MINV") && atoi(getenv("EGG_PGS_MINV")) == 2) DA(d.rec_minv, (size_t)W * d.nrec * 20);
+  if (dsc->solver == EGG_SOLVER_JACOBI || dsc->solver == EGG_SOLVER_SOR) {
+    DA(d.lam, (size_t)W * d.nrec * 3);
+    DA(d.lam2, (size_t)W * d.nrec * 3);
+    DA(d.slot_of, (size_t)W * d.nrec);
+  }
   DA(d.lam_out, (size_t)W * d.nrec * 3);
   DA(d.row_state, (size_t)W * d.nrec * 3);
-  if (dsc->solver == EGG_SOLVER_JACOBI || dsc->solver == EGG_SOLVER_SOR) DA(d.slot_of, (size_t)W * d.nrec);
-  DA(d.level_start, (size_t)W * (d.nrec + 1));
   DA(d.n_levels, W);
   DA(d.status, W);
   DA(d.stats, (size_t)W * 8);
@@ -196,13 +217,38 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   size_t jb = (size_t)W * (nj > 0 ? nj : 1) * 3 * sizeof(double);
   if (jb > b->stage_bytes) b->stage_bytes = jb;
   DA(b->stage, b->stage_bytes / sizeof(double));
+  // Shared-memory needs of every kernel this batch can launch, against the device limit: an
+  // unsupported shape fails here, not as a launch error inside the first egg_step.
+  {
+    int lim = 0;
+    CKB(cudaDeviceGetAttribute(&lim, cudaDevAttrMaxSharedMemoryPerBlockOptin, dsc->device));
+    struct { const char* what; size_t need; } req[4] = {
+        {"narrowphase (egg_collide_kernel)", egg_collide_smem(d)},
+        {"row assembly", d.rec_fmt ? (size_t)0 : egg_assemble_smem(d)},
+        {"PGS group stream", d.rec_fmt ? egg_stream_smem(d) : (size_t)0},
+        {"Jacobi / SOR", (dsc->solver == EGG_SOLVER_JACOBI || dsc->solver == EGG_SOLVER_SOR) ? egg_iter_smem(d) : (size_t)0}};
+    for (auto& r : req)
+      if (r.need > (size_t)lim) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "%s needs %zu bytes of shared memory per CTA for n_bodies = %d, max_contacts = %d; the device offers %d", r.what, r.need, n, maxc, lim);
+        g_err = buf;
+        egg_destroy(b);
+        return EGG_ERR_UNSUPPORTED;
+      }
+    if (dsc->solver == EGG_SOLVER_DENSE_MURTY && !egg_dense_smem_fits(d, (size_t)lim)) {
+      g_err = "dense solver: the row capacity (EGG_DENSE_ROWS / n_joints + 4 n_bodies constraints) does not fit the shared memory of one CTA";
+      egg_destroy(b);
+      return EGG_ERR_UNSUPPORTED;
+    }
+  }
   if (dsc->solver == EGG_SOLVER_DENSE_MURTY) {
+    DA(d.work, W);
     b->dense_scratch_bytes = egg_dense_scratch_bytes(d);
     char* p = nullptr;
     DA(p, b->dense_scratch_bytes);
     b->dense_scratch = p;
   }
-  CK(cudaStreamSynchronize(b->stream));
+  CKB(cudaStreamSynchronize(b->stream));
   *out = b;
   return EGG_OK;
 }
@@ -280,17 +326,15 @@ static int upload(egg_batch* b, const double* host, int per_world, int comps, do
   size_t bytes = (size_t)b->dev.W * per_world * comps * sizeof(double);
   if (bytes == 0) return EGG_OK;
   CK(cudaMemcpyAsync(b->stage, host, bytes, cudaMemcpyHostToDevice, b->stream));
-  egg_launch_pack(b->dev.W, b->stage, per_world, comps, soa, soa_comps, comp_off, b->stream);
+  LK(egg_launch_pack(b->dev.W, b->stage, per_world, comps, soa, soa_comps, comp_off, b->stream));
   b->launches++;
-  CK(cudaGetLastError());
   return EGG_OK;
 }
 static int download(egg_batch* b, double* host, int per_world, int comps, const double* soa, int soa_comps, int comp_off) {
   size_t bytes = (size_t)b->dev.W * per_world * comps * sizeof(double);
   if (bytes == 0) return EGG_OK;
-  egg_launch_unpack(b->dev.W, b->stage, per_world, comps, soa, soa_comps, comp_off, b->stream);
+  LK(egg_launch_unpack(b->dev.W, b->stage, per_world, comps, soa, soa_comps, comp_off, b->stream));
   b->launches++;
-  CK(cudaGetLastError());
   CK(cudaMemcpyAsync(host, b->stage, bytes, cudaMemcpyDeviceToHost, b->stream));
   // the staging buffer is reused by the next call
   CK(cudaStreamSynchronize(b->stream));
@@ -354,11 +398,48 @@ int egg_set_external(egg_batch* b, const double* f_ext) {
 int egg_init(egg_batch* b) {
   if (!b) return EGG_ERR_ARG;
   CK(cudaSetDevice(b->device));
-  egg_launch_init(b->dev, b->stream);
+  LK(egg_launch_init(b->dev, b->stream));
   b->launches += (b->dev.nj > 0) ? 3 : 2;
-  CK(cudaGetLastError());
+  // Ensemble::Init ends with CheckAndCorrectEnsembleState (ensembles.cc:28): the joint-joint
+  // conflict scan lives in the narrowphase kernel, so run it once here -- EGG_ST_JOINT_CONFLICT is
+  // then visible right after egg_init, as the reference's Panic would be.
+  LK(egg_launch_collide(b->dev, b->stream));
+  b->launches++;
   b->initialised = true;
   b->iso_known = false;
+  return EGG_OK;
+}
+
+// Shared by egg_init_stabilize / egg_post_stabilize: scratch and progress buffers, allocated once.
+static int relax_prepare(egg_batch* b) {
+  const int W = b->dev.W;
+  if (!b->dense_scratch) {
+    if (!egg_dense_smem_fits(b->dev, 227 * 1024)) { g_err = "stabilisation: the row capacity does not fit the shared memory of one CTA"; return EGG_ERR_UNSUPPORTED; }
+    b->dense_scratch_bytes = egg_dense_scratch_bytes(b->dev);
+    char* p = nullptr;
+    int r = dalloc(b, &p, b->dense_scratch_bytes);
+    if (r != EGG_OK) return r;
+    b->dense_scratch = p;
+  }
+  if (!b->relax_prog) {
+    int r = dalloc(b, &b->relax_prog, (size_t)2 * W); if (r != EGG_OK) return r;
+    r = dalloc(b, &b->relax_err2, (size_t)W); if (r != EGG_OK) return r;
+    r = dalloc(b, &b->relax_any, (size_t)1); if (r != EGG_OK) return r;
+  }
+  CK(cudaMemsetAsync(b->relax_prog, 0, (size_t)2 * W * sizeof(int), b->stream));
+  return EGG_OK;
+}
+static int relax_report(egg_batch* b, int* steps_out, double* err_sq_out) {
+  const int W = b->dev.W;
+  if (steps_out) {
+    std::vector<int> h((size_t)2 * W);
+    CK(cudaMemcpyAsync(h.data(), b->relax_prog, h.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    for (int w = 0; w < W; w++) steps_out[w] = h[2 * w];
+  }
+  if (err_sq_out) CK(cudaMemcpyAsync(err_sq_out, b->relax_err2, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  CK(cudaGetLastError());
   return EGG_OK;
 }
 
@@ -366,47 +447,50 @@ int egg_init_stabilize(egg_batch* b, int max_steps, int* steps_out, double* err_
   if (!b || max_steps < 0) return EGG_ERR_ARG;
   if (!b->initialised) { g_err = "egg_init_stabilize before egg_init"; return EGG_ERR_STATE; }
   CK(cudaSetDevice(b->device));
-  const int W = b->dev.W;
-  if (!b->dense_scratch) {
-    b->dense_scratch_bytes = egg_dense_scratch_bytes(b->dev);
-    char* p = nullptr;
-    int r = dalloc(b, &p, b->dense_scratch_bytes);
-    if (r != EGG_OK) return r;
-    b->dense_scratch = p;
-  }
-  int* prog = nullptr;
-  double* err2 = nullptr;
-  int* any = nullptr;
-  { int r = dalloc(b, &prog, (size_t)2 * W); if (r != EGG_OK) return r; }
-  { int r = dalloc(b, &err2, (size_t)W); if (r != EGG_OK) return r; }
-  { int r = dalloc(b, &any, (size_t)1); if (r != EGG_OK) return r; }
+  RET(relax_prepare(b));
   EggDev nodedup = b->dev;
   nodedup.prm.min_dist = -1.0;   // UpdateContacts only: the loop of ensembles.cc:610-617 never de-duplicates
-  nodedup.rec_fmt = 0;           // the relaxation kernel reads per-world records (the group stream is the PGS solver's)
+  nodedup.rec_fmt = 0;           // the relaxation kernel reads per-world records (dev.rec is large enough for either format)
+  nodedup.level_start = nullptr;
   const double dt = 0.001 * 500;   // kSimTimeStep * 500 (ensembles.cc:611)
   for (int it = 0; it <= max_steps; it++) {
-    egg_launch_collide(nodedup, b->stream);
-    egg_launch_assemble(nodedup, dt, b->stream);
-    CK(cudaMemsetAsync(any, 0, sizeof(int), b->stream));
-    egg_launch_relax(nodedup, dt, 0.2, max_steps, b->dense_scratch, prog, err2, any, b->stream);
+    LK(egg_launch_collide(nodedup, b->stream));
+    LK(egg_launch_assemble(nodedup, dt, b->stream));
+    CK(cudaMemsetAsync(b->relax_any, 0, sizeof(int), b->stream));
+    LK(egg_launch_relax(nodedup, dt, 0.2, max_steps, 0, b->dense_scratch, b->dense_scratch_bytes, b->relax_prog, b->relax_err2, b->relax_any, b->stream));
     b->launches += 3;
     int h_any = 0;
-    CK(cudaMemcpyAsync(&h_any, any, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(&h_any, b->relax_any, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
     if (!h_any) break;
   }
-  egg_launch_collide(b->dev, b->stream);   // CheckAndCorrectEnsembleState (ensembles.cc:618)
+  LK(egg_launch_collide(b->dev, b->stream));   // CheckAndCorrectEnsembleState (ensembles.cc:618)
   b->launches++;
-  if (steps_out) {
-    std::vector<int> h((size_t)2 * W);
-    CK(cudaMemcpyAsync(h.data(), prog, h.size() * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  return relax_report(b, steps_out, err_sq_out);
+}
+
+int egg_post_stabilize(egg_batch* b, int max_steps, int* steps_out, double* err_sq_out) {
+  if (!b || max_steps < 0) return EGG_ERR_ARG;
+  if (!b->initialised) { g_err = "egg_post_stabilize before egg_init"; return EGG_ERR_STATE; }
+  CK(cudaSetDevice(b->device));
+  RET(relax_prepare(b));
+  EggDev pw = b->dev;
+  pw.rec_fmt = 0;
+  pw.level_start = nullptr;
+  const double dt = 0.001 * 100;   // kSimTimeStep * 100 (ensembles.cc:634)
+  // ensembles.cc:624-645: the contact list is NOT refreshed inside this loop; the rows are rebuilt
+  // from the current body state and the stored contact geometry every iteration
+  for (int it = 0; it <= max_steps; it++) {
+    LK(egg_launch_assemble(pw, dt, b->stream));
+    CK(cudaMemsetAsync(b->relax_any, 0, sizeof(int), b->stream));
+    LK(egg_launch_relax(pw, dt, 0.2, max_steps, 1, b->dense_scratch, b->dense_scratch_bytes, b->relax_prog, b->relax_err2, b->relax_any, b->stream));
+    b->launches += 2;
+    int h_any = 0;
+    CK(cudaMemcpyAsync(&h_any, b->relax_any, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CK(cudaStreamSynchronize(b->stream));
-    for (int w = 0; w < W; w++) steps_out[w] = h[2 * w];
+    if (!h_any) break;
   }
-  if (err_sq_out) CK(cudaMemcpyAsync(err_sq_out, err2, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
-  CK(cudaGetLastError());
-  return EGG_OK;
+  return relax_report(b, steps_out, err_sq_out);
 }
 
 int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
@@ -445,15 +529,15 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     cudaError_t e__ = cudaStreamSynchronize(b->stream);                                      \
     if (e__ != cudaSuccess) { set_err(what, e__); return EGG_ERR_CUDA; }                      \
   }
-    egg_launch_collide(b->dev, b->stream);
+    LK(egg_launch_collide(b->dev, b->stream));
     DBG_SYNC("egg_collide_kernel")
     if (b->profiling) CK(cudaEventRecord(e[1], b->stream));
-    egg_launch_assemble(b->dev, dt, b->stream);
+    LK(egg_launch_assemble(b->dev, dt, b->stream));
     DBG_SYNC("assembly kernels")
     if (b->profiling) CK(cudaEventRecord(e[2], b->stream));
-    if (solver == EGG_SOLVER_PGS) egg_launch_solve_pgs(b->dev, dt, b->stream);
-    else if (solver == EGG_SOLVER_DENSE_MURTY) egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes);
-    else egg_launch_solve_iter(b->dev, dt, solver, b->stream);
+    if (solver == EGG_SOLVER_PGS) LK(egg_launch_solve_pgs(b->dev, dt, b->stream));
+    else if (solver == EGG_SOLVER_DENSE_MURTY) LK(egg_launch_solve_dense(b->dev, dt, b->stream, b->dense_scratch, b->dense_scratch_bytes));
+    else LK(egg_launch_solve_iter(b->dev, dt, solver, b->stream));
     DBG_SYNC("solve kernel")
 #undef DBG_SYNC
     if (b->profiling) CK(cudaEventRecord(e[3], b->stream));
@@ -467,9 +551,8 @@ int egg_update_contacts(egg_batch* b) {
   if (!b) return EGG_ERR_ARG;
   if (!b->initialised) { g_err = "egg_update_contacts before egg_init"; return EGG_ERR_STATE; }
   CK(cudaSetDevice(b->device));
-  egg_launch_collide(b->dev, b->stream);
+  LK(egg_launch_collide(b->dev, b->stream));
   b->launches++;
-  CK(cudaGetLastError());
   return EGG_OK;
 }
 
@@ -515,43 +598,57 @@ int egg_get_bodies(egg_batch* b, double* p, double* R, double* v, double* w) {
   return EGG_OK;
 }
 
-int egg_get_contacts(egg_batch* b, int* count, int* i0, int* i1, double* pos, double* nrm,
-                     double* depth, int* code, double* lambda, int* row_state) {
-  if (!b) return EGG_ERR_ARG;
+// Contact taps of worlds [first, first + count): the geometry is transposed from the device's
+// [world][7][max_contacts] layout to the host's [world][max_contacts][3] by the unpack kernel, in
+// chunks of as many worlds as fit the staging buffer (no host-side pass over the data).
+int egg_get_contacts_range(egg_batch* b, int first, int nworlds, int* count, int* i0, int* i1, double* pos, double* nrm,
+                           double* depth, int* code, double* lambda, int* row_state) {
+  if (!b || first < 0 || nworlds < 0 || first + nworlds > b->dev.W) return EGG_ERR_ARG;
   CK(cudaSetDevice(b->device));
   const EggDev& d = b->dev;
-  const size_t W = d.W, mc = d.maxc;
-  if (count) CK(cudaMemcpyAsync(count, d.c_count, W * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  if (i0) CK(cudaMemcpyAsync(i0, d.c_i0, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  if (i1) CK(cudaMemcpyAsync(i1, d.c_i1, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  if (code) CK(cudaMemcpyAsync(code, d.c_code, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  if (lambda) CK(cudaMemcpyAsync(lambda, d.lam_out, W * 3 * d.nrec * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-  if (row_state) CK(cudaMemcpyAsync(row_state, d.row_state, W * 3 * d.nrec * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaStreamSynchronize(b->stream));
+  const size_t W = (size_t)nworlds, mc = d.maxc, f = (size_t)first;
+  if (W == 0) return EGG_OK;
+  if (count) CK(cudaMemcpyAsync(count, d.c_count + f, W * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (i0) CK(cudaMemcpyAsync(i0, d.c_i0 + f * mc, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (i1) CK(cudaMemcpyAsync(i1, d.c_i1 + f * mc, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (code) CK(cudaMemcpyAsync(code, d.c_code + f * mc, W * mc * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+  if (lambda) CK(cudaMemcpyAsync(lambda, d.lam_out + f * 3 * d.nrec, W * 3 * d.nrec * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (row_state) CK(cudaMemcpyAsync(row_state, d.row_state + f * 3 * d.nrec, W * 3 * d.nrec * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   if (pos || nrm || depth) {
-    std::vector<double> g(W * 7 * mc);
-    CK(cudaMemcpyAsync(g.data(), d.c_geom, g.size() * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-    CK(cudaStreamSynchronize(b->stream));
-    for (size_t w = 0; w < W; w++)
-      for (size_t k = 0; k < mc; k++) {
-        const double* gw = g.data() + w * 7 * mc;
-        if (pos) for (int c = 0; c < 3; c++) pos[(w * mc + k) * 3 + c] = gw[c * mc + k];
-        if (nrm) for (int c = 0; c < 3; c++) nrm[(w * mc + k) * 3 + c] = gw[(3 + c) * mc + k];
-        if (depth) depth[w * mc + k] = gw[6 * mc + k];
+    size_t chunk = b->stage_bytes / (mc * 3 * sizeof(double));
+    if (chunk == 0) { g_err = "staging buffer smaller than one world's contact geometry"; return EGG_ERR_UNSUPPORTED; }
+    struct { double* host; int comps, off; } part[3] = {{pos, 3, 0}, {nrm, 3, 3}, {depth, 1, 6}};
+    for (size_t w0 = 0; w0 < W; w0 += chunk) {
+      const size_t nw = (W - w0 < chunk) ? W - w0 : chunk;
+      for (auto& pt : part) {
+        if (!pt.host) continue;
+        LK(egg_launch_unpack((int)nw, b->stage, (int)mc, pt.comps, d.c_geom + (f + w0) * 7 * mc, 7, pt.off, b->stream));
+        b->launches++;
+        CK(cudaMemcpyAsync(pt.host + w0 * mc * pt.comps, b->stage, nw * mc * pt.comps * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+        CK(cudaStreamSynchronize(b->stream));      // the staging buffer is reused by the next part
       }
+    }
   }
+  CK(cudaStreamSynchronize(b->stream));
   return EGG_OK;
 }
 
-int egg_get_pair_hits(egg_batch* b, int* n_hits, int* pi, int* pj, int* code, int* count, int max_pairs) {
-  if (!b || !n_hits) return EGG_ERR_ARG;
+int egg_get_contacts(egg_batch* b, int* count, int* i0, int* i1, double* pos, double* nrm,
+                     double* depth, int* code, double* lambda, int* row_state) {
+  if (!b) return EGG_ERR_ARG;
+  return egg_get_contacts_range(b, 0, b->dev.W, count, i0, i1, pos, nrm, depth, code, lambda, row_state);
+}
+
+int egg_get_pair_hits_range(egg_batch* b, int first, int nworlds, int* n_hits, int* pi, int* pj, int* code, int* count, int max_pairs) {
+  if (!b || !n_hits || first < 0 || nworlds < 0 || first + nworlds > b->dev.W) return EGG_ERR_ARG;
   const EggDev& d = b->dev;
   if (!d.pair_code) { g_err = "egg_get_pair_hits needs desc.taps = 1"; return EGG_ERR_STATE; }
   CK(cudaSetDevice(b->device));
-  const size_t W = d.W, P = d.P;
+  const size_t W = (size_t)nworlds, P = d.P, f = (size_t)first;
+  if (W == 0 || P == 0) { for (size_t w = 0; w < W; w++) n_hits[w] = 0; return EGG_OK; }
   std::vector<unsigned char> pc(W * P), pn(W * P);
-  CK(cudaMemcpyAsync(pc.data(), d.pair_code, W * P, cudaMemcpyDeviceToHost, b->stream));
-  CK(cudaMemcpyAsync(pn.data(), d.pair_cnt, W * P, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaMemcpyAsync(pc.data(), d.pair_code + f * P, W * P, cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaMemcpyAsync(pn.data(), d.pair_cnt + f * P, W * P, cudaMemcpyDeviceToHost, b->stream));
   CK(cudaStreamSynchronize(b->stream));
   for (size_t w = 0; w < W; w++) {
     int h = 0;
@@ -572,6 +669,11 @@ int egg_get_pair_hits(egg_batch* b, int* n_hits, int* pi, int* pj, int* code, in
   return EGG_OK;
 }
 
+int egg_get_pair_hits(egg_batch* b, int* n_hits, int* pi, int* pj, int* code, int* count, int max_pairs) {
+  if (!b) return EGG_ERR_ARG;
+  return egg_get_pair_hits_range(b, 0, b->dev.W, n_hits, pi, pj, code, count, max_pairs);
+}
+
 int egg_get_status(egg_batch* b, int* status, int* stats, double* residual) {
   if (!b) return EGG_ERR_ARG;
   CK(cudaSetDevice(b->device));
@@ -583,12 +685,20 @@ int egg_get_status(egg_batch* b, int* status, int* stats, double* residual) {
   return EGG_OK;
 }
 
+int egg_get_dense_work(egg_batch* b, double* flops) {
+  if (!b || !flops) return EGG_ERR_ARG;
+  if (!b->dev.work) { g_err = "egg_get_dense_work: the batch was not created with the dense solver"; return EGG_ERR_STATE; }
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpyAsync(flops, b->dev.work, (size_t)b->dev.W * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return EGG_OK;
+}
+
 int egg_rollout_costs(egg_batch* b, double* cost_d) {
   if (!b || !cost_d) return EGG_ERR_ARG;
   CK(cudaSetDevice(b->device));
-  egg_launch_costs(b->dev, cost_d, b->stream);
+  LK(egg_launch_costs(b->dev, cost_d, b->stream));
   b->launches++;
-  CK(cudaGetLastError());
   return EGG_OK;
 }
 

@@ -465,13 +465,21 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
 
 }  // namespace
 
-void egg_launch_collide(const EggDev& d, cudaStream_t s) {
-  size_t smem = (size_t)15 * d.n * sizeof(double) + (size_t)((d.P + 3) & ~3) * 2 + (size_t)((d.P + 7) & ~7);
+size_t egg_collide_smem(const EggDev& d) { return (size_t)15 * d.n * sizeof(double) + (size_t)((d.P + 3) & ~3) * 2 + (size_t)((d.P + 7) & ~7); }
+
+cudaError_t egg_launch_collide(const EggDev& d, cudaStream_t s) {
+  const size_t smem = egg_collide_smem(d);
+  cudaError_t e = cudaSuccess;
   if (d.n <= 16) {
     egg_collide_kernel<64><<<d.W, 64, smem, s>>>(d);
   } else {
-    if (smem > 48 * 1024)
-      cudaFuncSetAttribute(egg_collide_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static thread_local size_t attr_set = 0;       // the attribute only ever has to grow
+    if (smem > 48 * 1024 && smem > attr_set) {
+      e = cudaFuncSetAttribute(egg_collide_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set = smem;
+    }
     egg_collide_kernel<256><<<d.W, 256, smem, s>>>(d);
   }
+  return cudaGetLastError();
 }

@@ -1,231 +1,459 @@
 // Dense mixed-LCP path: what the reference actually ships in ComputeVDot.
 //
-// Replaces (per world, one CTA per world, working set in an L2-resident global scratch):
+// Replaces (per world):
 //   Ensemble::ComputeVDot            ensembles.cc:498-538   A = J M^-1 J^T (+ cfm I), solve, v_dot
 //   CheckMatrixCondition             utils.cc:256-287       "cond >= 1e7 => add cfm" decision
 //   Lcp::MixedConstraintsSolver      lcp.cc:276-336         Schur complement on the equality rows
 //   Lcp::MurtyPrincipalPivot         lcp.cc:157-274         least-index principal pivoting
 //   CheckMurtySolution / best-so-far lcp.cc:20-94,98-137
 //   Eigen LDLT<>::compute / solve    (lcp.cc:203,317)       restated as in oracle/orc_linalg.h
+//   dynamic MatrixXd::inverse()      (lcp.cc:293-294)       partial-pivot LU, as orc_linalg.h
 //   + v' = v + dt M^-1 (f + J^T x) and StepPositions_ODE    ensembles.cc:535,572-591
+//   Ensemble::CalculateVelocityRelaxation / StepPositionRelaxation / StepPostStabilization
+//                                    ensembles.cc:647-666   (egg_relax_kernel)
 //
-// The pivot sequence and the active set are discrete outputs compared bit-exactly with the oracle,
-// so every reduction whose result feeds a comparison is summed in the oracle's order (ascending
-// index, one accumulator) and this file is compiled with -fmad=false.
+// Execution model.  A persistent grid of 256-thread CTAs (two per SM) pulls worlds from an atomic
+// queue: the Murty loop takes 1 ... 1000 pivots depending on the world, so a static world -> CTA
+// map would leave most of the GPU idle behind the slowest worlds.  Every CTA owns one scratch slab
+// in global memory (A, the Schur complement, LU workspace: written once per step, L2 resident) and
+// keeps what the pivot loop touches hundreds of times in shared memory:
+//   * the LDL^T factor of the basic block A_SS as a packed lower triangle (k (k+1)/2 doubles;
+//     k <= ~145 rows fit next to the vectors, larger blocks fall back to the CTA's global slab),
+//   * x, w, the best-so-far pair, the right-hand side, the basic-set mask and index lists.
+//
+// Exactness.  The pivot sequence and the active set are discrete outputs that are compared
+// bit-exactly with the oracle, so every value that feeds a comparison is computed with the
+// oracle's operation order and this file is compiled with -fmad=false:
+//   * Eigen's LDLT pivots on the largest |diagonal| of the NOT-YET-UPDATED trailing part
+//     (orc_linalg.h LDLT::compute), so the whole pivot order is a function of the diagonal of the
+//     input alone: it is computed up front (order_by_diag: a parallel rank when all |d| differ, the
+//     swap-by-swap simulation otherwise), the lower triangle is gathered in pivoted order and the
+//     factorisation runs without data movement.  Every entry is the same left-looking dot product
+//     (ascending index, one accumulator) the oracle evaluates; rows run in parallel.
+//   * sums that decide something (goodness of an iterate) skip only exact zeros, which cannot
+//     change an IEEE sum that starts at +0.
+//   * the Schur complement follows lcp.cc:293-294 literally: LU inverse of A_ee, (A_ie A_ee^-1) A_ei
+//     with ascending-index dot products; structurally zero blocks of A_ie / A_ei are skipped (adding
+//     +-0 products is a no-op).
 //
 // Deviation (documented in DESIGN.md): the reference decides "add cfm" from a JacobiSVD condition
-// number (an O(rows^3) SVD per step).  Here the decision uses the pivot range of a diagonally
-// pivoted LDL^T of A (max |d| / min |d| >= 1e7, or a non-positive pivot).  The two agree whenever
-// the condition number is not within a small factor of 1e7; on the built-in scenes it is either
-// < 1e4 or > 1e15.
+// number (an O(rows^3) SVD with a large constant, every step).  Here the decision comes from a
+// diagonally pivoted LDL^T of A: its pivot range is a lower bound of cond_2(A) for a PSD matrix
+// (pivots are diagonal entries of Schur complements, which lie inside [lambda_min, lambda_max]),
+// so a range >= 1e7 means ill conditioned for certain; below that, lambda_max and lambda_min are
+// refined by power / inverse iteration with the same factor (cond_refine) until the estimate has
+// converged or crossed 1e7.  tests/test_gpu_parity.py::test_cfm_decision_sweep sweeps cond(A)
+// through 1e7 and reports where the two decisions part.
 #include "egg_internal.cuh"
+#include <cstdlib>
 
 namespace {
 
-constexpr int DT = 128;   // threads per CTA
+constexpr int DT = 256;   // threads per CTA
+constexpr int NWARP = DT / 32;
+constexpr unsigned FULL = 0xffffffffu;
+#define EGG_INF __longlong_as_double(0x7ff0000000000000LL)
 
-struct DenseScratch {
-  double* A;      // [R][R]
-  double* L;      // [I][I]   Schur complement (Murty's A)
-  double* F;      // [R][R]   factorisation workspace (>= max(E, I)^2)
-  double* X;      // [E][I+1] A_ee^-1 [A_ei | b_e]
-  double* Jb;     // [nc][2][18] Jacobian blocks, then [nc][2][18] J M^-1
-  double* vec;    // 12 vectors of length R
-  int* ivec;      // 4 int vectors of length R
+struct DenseCfg {
+  int Rcap;                // rows the path is provisioned for (multiple of 3)
+  int ncap;                // constraints = Rcap / 3
+  int Fcap;                // doubles of packed-factor storage in shared memory
+  size_t off_A, off_Wk, off_Lm, off_T1, off_Fg, off_Jb, off_vec, off_int;   // offsets into the CTA slab (doubles)
+  size_t per_cta;          // doubles per CTA slab
+  size_t smem;             // dynamic shared memory bytes
 };
 
-// ---- Eigen-style LDLT on a k x k matrix M (row-major, leading dimension ld), lower part used ----
-// tr[k] transpositions; tmp[k] scratch.  Mirrors orc::LDLT::compute.
-__device__ void ldlt_compute(double* M, int ld, int k, int* tr, double* tmp) {
-  const int tid = threadIdx.x;
-  __shared__ int s_big;
-  for (int kk = 0; kk < k; kk++) {
-    if (tid == 0) {
-      int big = kk;
-      double best = fabs(M[(size_t)kk * ld + kk]);
-      for (int i = kk + 1; i < k; i++) {
-        double v = fabs(M[(size_t)i * ld + i]);
-        if (v > best) { best = v; big = i; }
-      }
-      tr[kk] = big;
-      s_big = big;
-    }
-    __syncthreads();
-    const int big = s_big;
-    if (big != kk) {
-      for (int j = tid; j < kk; j += DT) { double t = M[(size_t)kk * ld + j]; M[(size_t)kk * ld + j] = M[(size_t)big * ld + j]; M[(size_t)big * ld + j] = t; }
-      for (int i = big + 1 + tid; i < k; i += DT) { double t = M[(size_t)i * ld + kk]; M[(size_t)i * ld + kk] = M[(size_t)i * ld + big]; M[(size_t)i * ld + big] = t; }
-      for (int i = kk + 1 + tid; i < big; i += DT) { double t = M[(size_t)i * ld + kk]; M[(size_t)i * ld + kk] = M[(size_t)big * ld + i]; M[(size_t)big * ld + i] = t; }
-      if (tid == 0) { double t = M[(size_t)kk * ld + kk]; M[(size_t)kk * ld + kk] = M[(size_t)big * ld + big]; M[(size_t)big * ld + big] = t; }
-      __syncthreads();
-    }
-    if (kk > 0) {
-      for (int j = tid; j < kk; j += DT) tmp[j] = M[(size_t)j * ld + j] * M[(size_t)kk * ld + j];
-      __syncthreads();
-      if (tid == 0) {
-        double s = 0;
-        for (int j = 0; j < kk; j++) s += M[(size_t)kk * ld + j] * tmp[j];
-        M[(size_t)kk * ld + kk] -= s;
-      }
-      for (int i = kk + 1 + tid; i < k; i += DT) {
-        double t = 0;
-        for (int j = 0; j < kk; j++) t += M[(size_t)i * ld + j] * tmp[j];
-        M[(size_t)i * ld + kk] -= t;
-      }
-      __syncthreads();
-    }
-    const double akk = M[(size_t)kk * ld + kk];
-    const bool valid = fabs(akk) > 0;
-    if (kk == 0 && !valid) {
-      for (int j = tid; j < k; j += DT) tr[j] = j;
-      __syncthreads();
-      return;
-    }
-    if (valid)
-      for (int i = kk + 1 + tid; i < k; i += DT) M[(size_t)i * ld + kk] /= akk;
-    __syncthreads();
-  }
+struct Sm {
+  double *x, *w, *bx, *bw, *rhs, *xs, *tmp;   // [Rcap] each
+  double* F;                                   // [Fcap] packed factor
+  double* sa;                                  // [6 n] a = M^-1 J^T lambda
+  unsigned short *sidx, *perm;                 // [Rcap]
+  unsigned char *S, *athi;                     // [Rcap]
+};
+
+__device__ __forceinline__ size_t tri(int i) { return (size_t)i * (size_t)(i + 1) / 2; }
+
+__device__ Sm carve(unsigned char* raw, const DenseCfg& c, int n) {
+  Sm s;
+  double* p = reinterpret_cast<double*>(raw);
+  s.x = p; p += c.Rcap; s.w = p; p += c.Rcap; s.bx = p; p += c.Rcap; s.bw = p; p += c.Rcap;
+  s.rhs = p; p += c.Rcap; s.xs = p; p += c.Rcap; s.tmp = p; p += c.Rcap;
+  s.sa = p; p += 6 * n;
+  s.F = p; p += c.Fcap;
+  s.sidx = reinterpret_cast<unsigned short*>(p);
+  s.perm = s.sidx + c.Rcap;
+  s.S = reinterpret_cast<unsigned char*>(s.perm + c.Rcap);
+  s.athi = s.S + c.Rcap;
+  return s;
 }
 
-// x <- solve(M factor, x) in place (x length k).  Mirrors orc::LDLT::solve.
-__device__ void ldlt_solve(const double* M, int ld, int k, const int* tr, double* x) {
+// ---- ordered compaction of the flags equal to `want` -> ascending index list; returns the count
+__device__ int build_index_list(const unsigned char* flag, int want, int len, unsigned short* out) {
+  __shared__ int s_cnt[NWARP];
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  int base = 0;
+  for (int c0 = 0; c0 < len; c0 += DT) {
+    const int i = c0 + tid;
+    const bool f = i < len && (flag[i] != 0) == (want != 0);
+    const unsigned m = __ballot_sync(FULL, f);
+    if (lane == 0) s_cnt[wp] = __popc(m);
+    __syncthreads();
+    int off = base, tot = 0;
+#pragma unroll
+    for (int q = 0; q < NWARP; q++) { const int c = s_cnt[q]; if (q < wp) off += c; tot += c; }
+    if (f) out[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+    base += tot;
+    __syncthreads();
+  }
+  return base;
+}
+
+// ---- pivot order of Eigen's LDLT from the |diagonal| alone -----------------------------------
+// dabs[k] (shared) = |diagonal| by element; perm[pos] = element chosen at step pos.  Mirrors the
+// selection of orc::LDLT::compute: at step kk the FIRST position >= kk holding the largest value
+// wins and is swapped with position kk.  With all values distinct that is the descending sort;
+// ties take the swap-by-swap simulation (warp 0; dabs is permuted along).
+__device__ void order_by_diag(double* dabs, int k, unsigned short* perm) {
   const int tid = threadIdx.x;
-  if (tid == 0)
-    for (int i = 0; i < k; i++) if (tr[i] != i) { double t = x[i]; x[i] = x[tr[i]]; x[tr[i]] = t; }
+  int tie = 0;
+  for (int e = tid; e < k; e += DT) {
+    const double v = dabs[e];
+    int gt = 0;
+    for (int f = 0; f < k; f++) {
+      const double u = dabs[f];
+      gt += (u > v);
+      tie |= (u == v) && (f != e);
+    }
+    perm[gt] = (unsigned short)e;    // a permutation iff there are no ties
+  }
+  if (!__syncthreads_or(tie)) return;
+  if (tid < 32) {
+    const int lane = tid;
+    for (int e = lane; e < k; e += 32) perm[e] = (unsigned short)e;
+    __syncwarp();
+    for (int kk = 0; kk < k; kk++) {
+      double best = -1.0;
+      int bp = k;
+      for (int p = kk + lane; p < k; p += 32) {
+        const double v = dabs[p];
+        if (v > best) { best = v; bp = p; }      // ascending p per lane: first max of the lane
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(FULL, best, o);
+        const int op = __shfl_xor_sync(FULL, bp, o);
+        if (ob > best || (ob == best && op < bp)) { best = ob; bp = op; }
+      }
+      if (lane == 0 && bp != kk && bp < k) {
+        const double tv = dabs[kk]; dabs[kk] = dabs[bp]; dabs[bp] = tv;
+        const unsigned short te = perm[kk]; perm[kk] = perm[bp]; perm[bp] = te;
+      }
+      __syncwarp();
+    }
+  }
   __syncthreads();
-  for (int i = 0; i < k; i++) {            // L^-1, column-oriented: same per-entry operation order
-    const double xi = x[i];
-    for (int r = i + 1 + tid; r < k; r += DT) x[r] -= M[(size_t)r * ld + i] * xi;
+}
+
+// ---- packed LDL^T: gather, factor, solve ------------------------------------------------------
+// Source matrix M (row-major, leading dimension ld, global); element e of the block is row/column
+// idx[e] of M (idx == nullptr: e itself).  The factor of the symmetrically permuted block is built
+// from M's LOWER triangle, exactly as Eigen's in-place swaps do (orc::LDLT::compute).
+__device__ void ldlt_gather(const double* __restrict__ M, int ld, const unsigned short* idx, const unsigned short* perm, int k, double* F) {
+  const int total = (int)tri(k);
+  for (int e = threadIdx.x; e < total; e += DT) {
+    int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+    while ((int)tri(i + 1) <= e) i++;
+    while ((int)tri(i) > e) i--;
+    const int j = e - (int)tri(i);
+    int a = perm[i], b = perm[j];
+    if (idx) { a = idx[a]; b = idx[b]; }
+    const int r = a > b ? a : b, c = a > b ? b : a;
+    F[e] = M[(size_t)r * ld + c];
+  }
+  __syncthreads();
+}
+
+// In-place left-looking factorisation of the packed lower triangle F (k x k): on exit F holds L
+// strictly below the diagonal and D on it; tmp[k] is scratch.  Per entry: t = sum_j L[i][j] *
+// (D[j] L[kk][j]) for ascending j from 0, then A[i][kk] - t, then / D[kk]: orc::LDLT::compute.
+// Two barriers per column.
+__device__ void ldlt_factor(double* F, int k, double* tmp) {
+  const int tid = threadIdx.x;
+  for (int kk = 0; kk < k; kk++) {
+    const double* rk = F + tri(kk);
+    if (kk > 0) {
+      // temp[j] = D[j] L[kk][j]; entry kk-1 was written by the thread that closed column kk-1 (below)
+      for (int j = tid; j < kk - 1; j += DT) tmp[j] = F[tri(j) + j] * rk[j];
+      __syncthreads();
+      for (int i = kk + tid; i < k; i += DT) {
+        const double* ri = F + tri(i);
+        double t = 0;
+        int j = 0;
+        for (; j + 4 <= kk; j += 4) {
+          const double a0 = ri[j] * tmp[j], a1 = ri[j + 1] * tmp[j + 1], a2 = ri[j + 2] * tmp[j + 2], a3 = ri[j + 3] * tmp[j + 3];
+          t += a0; t += a1; t += a2; t += a3;
+        }
+        for (; j < kk; j++) t += ri[j] * tmp[j];
+        F[tri(i) + kk] -= t;
+      }
+      __syncthreads();
+    }
+    const double akk = F[tri(kk) + kk];
+    const bool valid = fabs(akk) > 0;
+    if (kk == 0 && !valid) break;                      // orc::LDLT::compute: matrix left as it is
+    for (int i = kk + 1 + tid; i < k; i += DT) {
+      double v = F[tri(i) + kk];
+      if (valid) { v /= akk; F[tri(i) + kk] = v; }
+      if (i == kk + 1) tmp[kk] = akk * v;              // the temp entry of the next column that needs this division
+    }
+    // the barrier at the top of the next column orders these writes before their use
+  }
+  __syncthreads();
+}
+
+// x <- L^-T D^+ L^-1 x for x in PIVOTED order (x[pos] belongs to element perm[pos]); the caller
+// applies the transpositions by gathering / scattering through perm.  orc::LDLT::solve: forward
+// row i receives its terms for ascending j, the backward sweep is the column form.
+__device__ void ldlt_solve(const double* F, int k, double* x) {
+  const int tid = threadIdx.x;
+  for (int j = 0; j + 1 < k; j++) {
+    const double xj = x[j];
+    for (int i = j + 1 + tid; i < k; i += DT) x[i] -= F[tri(i) + j] * xj;
     __syncthreads();
   }
   const double tol = 1.0 / 1.7976931348623157e308;
   for (int i = tid; i < k; i += DT) {
-    const double dd = M[(size_t)i * ld + i];
+    const double dd = F[tri(i) + i];
     x[i] = (fabs(dd) > tol) ? x[i] / dd : 0.0;
   }
   __syncthreads();
-  for (int i = k - 1; i >= 0; i--) {       // L^-T
-    const double xi = x[i];
-    for (int r = tid; r < i; r += DT) x[r] -= M[(size_t)i * ld + r] * xi;
+  for (int j = k - 1; j >= 1; j--) {
+    const double xj = x[j];
+    const double* rj = F + tri(j);
+    for (int i = tid; i < j; i += DT) x[i] -= rj[i] * xj;
     __syncthreads();
   }
-  if (tid == 0)
-    for (int i = k - 1; i >= 0; i--) if (tr[i] != i) { double t = x[i]; x[i] = x[tr[i]]; x[tr[i]] = t; }
-  __syncthreads();
 }
 
-// X[:, j] <- solve(M factor, X[:, j]) for ncols right-hand sides stored as columns of X (row
-// stride ldx).  One thread per column runs the whole substitution for it: the per-entry operation
-// order is that of ldlt_solve (so the results are the same bits), the threads read M as a
-// broadcast and X coalesced, and there is no barrier inside (the one-RHS-at-a-time form cost
-// 2k barriers per right-hand side: 37 000 for the Schur complement of a 32-link chain).
-__device__ void ldlt_solve_columns(const double* M, int ld, int k, const int* tr, double* X, int ldx, int ncols) {
-  const double tol = 1.0 / 1.7976931348623157e308;
-  for (int j = threadIdx.x; j < ncols; j += DT) {
-    double* x = X + j;
-    for (int i = 0; i < k; i++) if (tr[i] != i) { double t = x[(size_t)i * ldx]; x[(size_t)i * ldx] = x[(size_t)tr[i] * ldx]; x[(size_t)tr[i] * ldx] = t; }
-    for (int i = 0; i < k; i++) {            // L^-1
-      const double xi = x[(size_t)i * ldx];
-      for (int r = i + 1; r < k; r++) x[(size_t)r * ldx] -= M[(size_t)r * ld + i] * xi;
-    }
-    for (int i = 0; i < k; i++) {
-      const double dd = M[(size_t)i * ld + i];
-      x[(size_t)i * ldx] = (fabs(dd) > tol) ? x[(size_t)i * ldx] / dd : 0.0;
-    }
-    for (int i = k - 1; i >= 0; i--) {       // L^-T
-      const double xi = x[(size_t)i * ldx];
-      for (int r = 0; r < i; r++) x[(size_t)r * ldx] -= M[(size_t)i * ld + r] * xi;
-    }
-    for (int i = k - 1; i >= 0; i--) if (tr[i] != i) { double t = x[(size_t)i * ldx]; x[(size_t)i * ldx] = x[(size_t)tr[i] * ldx]; x[(size_t)tr[i] * ldx] = t; }
+// Factor the k x k block of M selected by idx (ascending element list, or nullptr) into Fuse
+// (shared if it fits, else the global slab) and return the storage used.  dabs / perm: shared [k].
+__device__ double* ldlt_block(const double* M, int ld, const unsigned short* idx, int k, const Sm& sm, const DenseCfg& cfg, double* Fg) {
+  for (int e = threadIdx.x; e < k; e += DT) {
+    const int g = idx ? idx[e] : e;
+    sm.tmp[e] = fabs(M[(size_t)g * ld + g]);
   }
   __syncthreads();
+  order_by_diag(sm.tmp, k, sm.perm);
+  __syncthreads();
+  double* F = ((size_t)tri(k) <= (size_t)cfg.Fcap) ? sm.F : Fg;
+  ldlt_gather(M, ld, idx, sm.perm, k, F);
+  ldlt_factor(F, k, sm.tmp);
+  return F;
 }
 
-// Pivot range of a complete-diagonal-pivoted LDL^T (right-looking, updated diagonal): the
-// "is A ill conditioned" proxy.  Destroys M.  Returns true if well conditioned (ratio < 1e7).
-__device__ bool well_conditioned(double* M, int ld, int k) {
-  const int tid = threadIdx.x;
-  __shared__ int s_piv;
+// ---- cfm decision ------------------------------------------------------------------------------
+// Complete-diagonal-pivoted LDL^T of the symmetric PSD matrix M (R x R, global, both triangles
+// kept up to date), right-looking.  Returns 0 = ill conditioned for certain (pivot range >= 1e7 or
+// a non-positive pivot), 1 = factorisation completed; then *lb = pivot range, piv[] = pivot
+// sequence, M holds the factor (column kk below the diagonal = L[:,kk] * d_kk, row kk right of the
+// diagonal likewise, d on the diagonal) in pivoted coordinates.
+__device__ int pivoted_ldlt_range(double* M, int R, unsigned short* piv, double* lb) {
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  __shared__ double s_val[NWARP];
+  __shared__ int s_idx[NWARP];
   __shared__ double s_dmax, s_dmin;
-  __shared__ int s_bad;
-  if (tid == 0) { s_dmax = 0; s_dmin = 1.7976931348623157e308; s_bad = 0; }
+  __shared__ int s_big;
+  if (tid == 0) { s_dmax = 0; s_dmin = 1.7976931348623157e308; }
   __syncthreads();
-  for (int kk = 0; kk < k; kk++) {
+  for (int kk = 0; kk < R; kk++) {
+    double best = -1.7976931348623157e308;
+    int bi = R;
+    for (int i = kk + tid; i < R; i += DT) { const double v = M[(size_t)i * R + i]; if (v > best) { best = v; bi = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULL, best, o);
+      const int oi = __shfl_xor_sync(FULL, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { s_val[wp] = best; s_idx[wp] = bi; }
+    __syncthreads();
     if (tid == 0) {
-      int big = kk;
-      double best = M[(size_t)kk * ld + kk];
-      for (int i = kk + 1; i < k; i++) { double v = M[(size_t)i * ld + i]; if (v > best) { best = v; big = i; } }
-      s_piv = big;
-      if (!(best > 0)) s_bad = 1;
-      else { if (best > s_dmax) s_dmax = best; if (best < s_dmin) s_dmin = best; }
+      double b = s_val[0]; int ix = s_idx[0];
+      for (int q = 1; q < NWARP; q++) if (s_val[q] > b || (s_val[q] == b && s_idx[q] < ix)) { b = s_val[q]; ix = s_idx[q]; }
+      s_big = ix;
+      piv[kk] = (unsigned short)ix;
+      if (!(b > 0)) s_big = -1;
+      else { if (b > s_dmax) s_dmax = b; if (b < s_dmin) s_dmin = b; }
     }
     __syncthreads();
-    if (s_bad) return false;
-    if (s_dmax >= 1e7 * s_dmin) return false;
-    const int big = s_piv;
+    const int big = s_big;
+    if (big < 0 || s_dmax >= 1e7 * s_dmin) return 0;
     if (big != kk) {   // full symmetric swap (both triangles kept)
-      for (int j = tid; j < k; j += DT) { double t = M[(size_t)kk * ld + j]; M[(size_t)kk * ld + j] = M[(size_t)big * ld + j]; M[(size_t)big * ld + j] = t; }
+      for (int j = tid; j < R; j += DT) { double t = M[(size_t)kk * R + j]; M[(size_t)kk * R + j] = M[(size_t)big * R + j]; M[(size_t)big * R + j] = t; }
       __syncthreads();
-      for (int i = tid; i < k; i += DT) { double t = M[(size_t)i * ld + kk]; M[(size_t)i * ld + kk] = M[(size_t)i * ld + big]; M[(size_t)i * ld + big] = t; }
+      for (int i = tid; i < R; i += DT) { double t = M[(size_t)i * R + kk]; M[(size_t)i * R + kk] = M[(size_t)i * R + big]; M[(size_t)i * R + big] = t; }
       __syncthreads();
     }
     // trailing update, one column j per thread (coalesced across the threads, the multiplier
-    // column M[i][kk] is a broadcast): no integer or floating-point division in the k^3/3 loop.
-    // Only the pivot RANGE of this factorisation is used (a yes/no decision), so the rounding of
-    // a * b / d versus a * (b / d) is immaterial.
-    const double invd = 1.0 / M[(size_t)kk * ld + kk];
-    for (int j = kk + 1 + tid; j < k; j += DT) {
-      const double ukj = M[(size_t)kk * ld + j] * invd;
-      for (int i = kk + 1; i < k; i++) M[(size_t)i * ld + j] -= M[(size_t)i * ld + kk] * ukj;
+    // column M[i][kk] is a broadcast)
+    const double invd = 1.0 / M[(size_t)kk * R + kk];
+    for (int j = kk + 1 + tid; j < R; j += DT) {
+      const double ukj = M[(size_t)kk * R + j] * invd;
+      for (int i = kk + 1; i < R; i++) M[(size_t)i * R + j] -= M[(size_t)i * R + kk] * ukj;
     }
     __syncthreads();
   }
-  return true;
+  *lb = s_dmax / s_dmin;
+  return 1;
 }
 
-// lcp.cc:20-94 with x_lo / x_hi per row; Cx[i] = bound at which a non-basic x(i) sits.
-// Returns 1 = solution, 0 = not a solution (S possibly flipped at the least offending index).
-__device__ int check_murty(const double* A, int ld, int dim, const double* b, const double* x, const double* w, unsigned char* S,
-                           double* Cx, const double* lo, const double* hi, double err, double* tmp) {
+// y = A x for the symmetric R x R matrix A in global memory (thread per row), x and y shared.
+__device__ void sym_matvec(const double* __restrict__ A, int R, const double* x, double* y) {
+  for (int i = threadIdx.x; i < R; i += DT) {
+    double s = 0;
+    for (int j = 0; j < R; j++) s += A[(size_t)j * R + i] * x[j];   // column i = row i (symmetric): coalesced over the threads
+    y[i] = s;
+  }
+  __syncthreads();
+}
+__device__ double block_norm2(const double* v, int R, double* red) {
+  const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+  double s = 0;
+  for (int i = tid; i < R; i += DT) s += v[i] * v[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  __syncthreads();
+  if (lane == 0) red[wp] = s;
+  __syncthreads();
+  double t = 0;
+  for (int q = 0; q < NWARP; q++) t += red[q];
+  __syncthreads();
+  return t;
+}
+// z <- (P^T L D L^T P)^-1 z with the factor left in M by pivoted_ldlt_range (pivoted coordinates:
+// the swaps were applied to the matrix, so z is swapped along).
+__device__ void pivoted_solve(const double* M, int R, const unsigned short* piv, double* z) {
+  const int tid = threadIdx.x;
+  if (tid == 0)
+    for (int k = 0; k < R; k++) { const int p = piv[k]; if (p != k) { const double t = z[k]; z[k] = z[p]; z[p] = t; } }
+  __syncthreads();
+  for (int k = 0; k + 1 < R; k++) {                     // L^-1 (L[:,k] = M[:,k] / d_k)
+    const double zk = z[k] / M[(size_t)k * R + k];
+    for (int i = k + 1 + tid; i < R; i += DT) z[i] -= M[(size_t)k * R + i] * zk;   // row k right of the diagonal = column k below it
+    __syncthreads();
+  }
+  for (int i = tid; i < R; i += DT) z[i] /= M[(size_t)i * R + i];
+  __syncthreads();
+  for (int k = R - 1; k >= 1; k--) {                    // L^-T
+    const double zk = z[k];
+    for (int i = tid; i < k; i += DT) z[i] -= (M[(size_t)i * R + k] / M[(size_t)i * R + i]) * zk;
+    __syncthreads();
+  }
+  if (tid == 0)
+    for (int k = R - 1; k >= 0; k--) { const int p = piv[k]; if (p != k) { const double t = z[k]; z[k] = z[p]; z[p] = t; } }
+  __syncthreads();
+}
+// cond_2(A) = lambda_max / lambda_min by power iteration on A and inverse iteration on its factor.
+// Both Rayleigh quotients approach their eigenvalue from inside the spectrum, so the running
+// estimate grows towards cond_2(A): crossing 1e7 decides "ill conditioned"; convergence of both
+// quotients (relative change < 1e-10 twice in a row) below 1e7 decides "well conditioned".
+__device__ bool cond_refine_is_good(const double* A, const double* Mf, int R, const unsigned short* piv, double* u, double* v, double* y, double* red) {
+  for (int i = threadIdx.x; i < R; i += DT) { u[i] = 1.0 + 0.37 * (double)((i * 7919) % 13); v[i] = 1.0 + 0.29 * (double)((i * 104729) % 11); }
+  __syncthreads();
+  double lmax = 0, lmin_inv = 0;
+  int calm = 0;
+  for (int it = 0; it < 400; it++) {
+    // power step on A
+    const double nu = sqrt(block_norm2(u, R, red));
+    for (int i = threadIdx.x; i < R; i += DT) u[i] /= nu;
+    __syncthreads();
+    sym_matvec(A, R, u, y);
+    double q = 0;
+    { double s = 0; for (int i = threadIdx.x; i < R; i += DT) s += u[i] * y[i];
+      const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+      __syncthreads();
+      if (lane == 0) red[wp] = s;
+      __syncthreads();
+      for (int k = 0; k < NWARP; k++) q += red[k];
+      __syncthreads(); }
+    for (int i = threadIdx.x; i < R; i += DT) u[i] = y[i];
+    __syncthreads();
+    // inverse step on the factor: Rayleigh quotient of A^-1
+    const double nv = sqrt(block_norm2(v, R, red));
+    for (int i = threadIdx.x; i < R; i += DT) { v[i] /= nv; y[i] = v[i]; }
+    __syncthreads();
+    pivoted_solve(Mf, R, piv, y);
+    double qi = 0;
+    { double s = 0; for (int i = threadIdx.x; i < R; i += DT) s += v[i] * y[i];
+      const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+      __syncthreads();
+      if (lane == 0) red[wp] = s;
+      __syncthreads();
+      for (int k = 0; k < NWARP; k++) qi += red[k];
+      __syncthreads(); }
+    for (int i = threadIdx.x; i < R; i += DT) v[i] = y[i];
+    __syncthreads();
+    const bool settled = fabs(q - lmax) <= 1e-10 * fabs(q) && fabs(qi - lmin_inv) <= 1e-10 * fabs(qi);
+    lmax = q; lmin_inv = qi;
+    if (lmax * lmin_inv >= 1e7) return false;
+    calm = settled ? calm + 1 : 0;
+    if (calm >= 2) return true;
+  }
+  return lmax * lmin_inv < 1e7;
+}
+
+// ---- lcp.cc:20-94 -------------------------------------------------------------------------------
+// Bounds of inequality row i: [0, inf) under quirk q1 (and on every normal row), [-1, 1] on the
+// two tangential rows of a contact otherwise.
+__device__ __forceinline__ double row_lo(int i, bool boxed) { return (boxed && (i % 3) < 2) ? -1.0 : 0.0; }
+__device__ __forceinline__ double row_hi(int i, bool boxed) { return (boxed && (i % 3) < 2) ? 1.0 : EGG_INF; }
+
+// Returns 1 = solution, 0 = not a solution (S flipped at the least offending index, if any).
+__device__ int check_murty(const double* __restrict__ A, int dim, const Sm& sm, const double* x, const double* w, bool boxed, double err) {
   const int tid = threadIdx.x;
   __shared__ int s_first, s_result;
   if (tid == 0) { s_first = dim; s_result = -1; }
   __syncthreads();
   int mine = dim;
   for (int i = tid; i < dim; i += DT) {
+    const double lo = row_lo(i, boxed), hi = row_hi(i, boxed);
     bool viol;
-    if (S[i]) viol = (x[i] < lo[i]) || (x[i] > hi[i]);
-    else viol = (Cx[i] == lo[i] && w[i] < 0) || (Cx[i] == hi[i] && w[i] > 0);
+    if (sm.S[i]) viol = (x[i] < lo) || (x[i] > hi);
+    else viol = (!sm.athi[i] && w[i] < 0) || (sm.athi[i] && w[i] > 0);
     if (viol) { mine = i; break; }
   }
   if (mine < dim) atomicMin(&s_first, mine);
   __syncthreads();
-  if (s_first < dim) {
+  const int first = s_first;
+  if (first < dim) {
     if (tid == 0) {
-      const int i = s_first;
-      if (S[i]) { S[i] = 0; Cx[i] = (x[i] < lo[i]) ? lo[i] : hi[i]; }
-      else S[i] = 1;
+      if (sm.S[first]) { sm.S[first] = 0; sm.athi[first] = (x[first] < row_lo(first, boxed)) ? 0 : 1; }
+      else sm.S[first] = 1;
     }
     __syncthreads();
     return 0;
   }
-  // goodness checks
   int bad = 0;
   for (int i = tid; i < dim; i += DT) {
-    if (x[i] < lo[i] || x[i] > hi[i]) bad = 1;
-    if (x[i] == lo[i] && w[i] < 0) bad = 1;
-    if (x[i] == hi[i] && w[i] > 0) bad = 1;
+    const double lo = row_lo(i, boxed), hi = row_hi(i, boxed);
+    if (x[i] < lo || x[i] > hi) bad = 1;
+    if (x[i] == lo && w[i] < 0) bad = 1;
+    if (x[i] == hi && w[i] > 0) bad = 1;
   }
   if (__syncthreads_or(bad)) return 0;
   for (int i = tid; i < dim; i += DT) {
     double s = 0;
-    for (int j = 0; j < dim; j++) s += A[(size_t)i * ld + j] * x[j];
-    tmp[i] = s - (b[i] + w[i]);
+    for (int j = 0; j < dim; j++) s += A[(size_t)i * dim + j] * x[j];
+    sm.tmp[i] = s - (sm.rhs[i] + w[i]);
   }
   __syncthreads();
   if (tid == 0) {
     double s = 0;
-    for (int i = 0; i < dim; i++) s += tmp[i] * tmp[i];
+    for (int i = 0; i < dim; i++) s += sm.tmp[i] * sm.tmp[i];
     const double chk = fabs(err) > 1e-9 ? fabs(err) : 1e-9;
     s_result = (sqrt(s) > chk) ? 0 : 1;
   }
@@ -233,281 +461,30 @@ __device__ int check_murty(const double* A, int ld, int dim, const double* b, co
   return s_result;
 }
 
-__global__ void __launch_bounds__(DT) egg_dense_kernel(EggDev d, double dt, double* scratch, size_t per_world, int Rcap) {
-  const int w = blockIdx.x, tid = threadIdx.x, n = d.n, nj = d.nj;
-  const int nc = nj + d.c_count[w];
-  int R = 3 * nc;
-  const int E = 3 * nj;
-  __shared__ int s_flag;
-  extern __shared__ double sa[];   // [6][n] accumulator a = M^-1 J^T lambda
-  for (int i = tid; i < 6 * n; i += DT) sa[i] = 0.0;
-  const double* st = d.stat + (size_t)w * EGG_STAT * n;
-  double* lam_out = d.lam_out + (size_t)w * 3 * d.nrec;
-  int* rs_out = d.row_state + (size_t)w * 3 * d.nrec;
-  int* stt = d.stats + (size_t)w * 8;
-  bool overflow = false;
-  if (R > Rcap) { overflow = true; R = 0; }
-  const int I = R - (R ? E : 0);
-  int pivots = 0, cfm_applied = 0, lcp_failed = 0;
-
-  if (R > 0) {
-    double* base = scratch + (size_t)w * per_world;
-    double* A = base;
-    double* L = A + (size_t)Rcap * Rcap;
-    double* F = L + (size_t)Rcap * Rcap;
-    double* X = F + (size_t)Rcap * Rcap;
-    double* Jb = X + (size_t)Rcap * (Rcap + 1);
-    double* vec = Jb + (size_t)(Rcap / 3 + 1) * 72;
-    double* b = vec;                 // rhs [R]
-    double* x = vec + Rcap;          // Murty x [I]
-    double* wv = vec + 2 * Rcap;     // Murty w [I]
-    double* bx = vec + 3 * Rcap;
-    double* bw = vec + 4 * Rcap;
-    double* lo = vec + 5 * Rcap;
-    double* hi = vec + 6 * Rcap;
-    double* Cx = vec + 7 * Rcap;
-    double* tmp = vec + 8 * Rcap;
-    double* xs = vec + 9 * Rcap;     // sub-system rhs / solution
-    double* rhsL = vec + 10 * Rcap;  // Schur rhs [I]
-    double* lamv = vec + 11 * Rcap;  // final lambda [R], reference row order
-    int* ivec = reinterpret_cast<int*>(base + per_world) - 4 * Rcap;
-    int* tr = ivec;
-    int* sidx = ivec + Rcap;
-    int* ci0 = ivec + 2 * Rcap;      // body indices per constraint (reference order)
-    int* ci1 = ivec + 3 * Rcap;
-    unsigned char* S = reinterpret_cast<unsigned char*>(ivec) - Rcap;   // basic-set mask, just below the int vectors in the tail
-
-    // ---- 1. Jacobian blocks per constraint in REFERENCE order (records are in level order) ----
-    const double* recs = d.rec + (size_t)w * d.nrec * EGG_REC;
-    for (int s = tid; s < nc; s += DT) {
-      const double* r = recs + (size_t)s * EGG_REC;
-      const int i0 = __double2loint(r[REC_IDX]), i1 = __double2hiint(r[REC_IDX]);
-      const int c = __double2loint(r[REC_META]);
-      ci0[c] = i0; ci1[c] = i1;
-      d3 r0 = mk3(r[REC_R0], r[REC_R0 + 1], r[REC_R0 + 2]), r1 = mk3(r[REC_R1], r[REC_R1 + 1], r[REC_R1 + 2]);
-      double* J0 = Jb + (size_t)c * 72;
-      double* J1 = J0 + 18;
-      double* B0 = J0 + 36;
-      double* B1 = J0 + 54;
-      for (int k = 0; k < 3; k++) {
-        d3 rc = mk3(r[REC_RC + 3 * k], r[REC_RC + 3 * k + 1], r[REC_RC + 3 * k + 2]);
-        d3 a0 = cross3(rc, r0), a1 = cross3(r1, rc);
-        J0[6 * k] = -rc.x; J0[6 * k + 1] = -rc.y; J0[6 * k + 2] = -rc.z; J0[6 * k + 3] = a0.x; J0[6 * k + 4] = a0.y; J0[6 * k + 5] = a0.z;
-        J1[6 * k] = rc.x; J1[6 * k + 1] = rc.y; J1[6 * k + 2] = rc.z; J1[6 * k + 3] = a1.x; J1[6 * k + 4] = a1.y; J1[6 * k + 5] = a1.z;
-        b[3 * c + k] = r[REC_RHS + k];
-      }
-      for (int side = 0; side < 2; side++) {
-        const int bd = side ? i1 : i0;
-        const double* Jx = side ? J1 : J0;
-        double* Bx = side ? B1 : B0;
-        if (bd < 0) { for (int q = 0; q < 18; q++) Bx[q] = 0.0; continue; }
-        const double mi = st[bd];
-        double Ii[9];
-        for (int q = 0; q < 9; q++) Ii[q] = st[(1 + q) * n + bd];
-        for (int k = 0; k < 3; k++) {       // (J * M^-1) row k
-          for (int q = 0; q < 3; q++) Bx[6 * k + q] = Jx[6 * k + q] * mi;
-          for (int q = 0; q < 3; q++) {
-            double s2 = 0;
-            for (int t = 0; t < 3; t++) s2 += Jx[6 * k + 3 + t] * Ii[3 * t + q];
-            Bx[6 * k + 3 + q] = s2;
-          }
-        }
-      }
-      // bounds of the rows of c: joints are equalities; contacts [0,inf) under q1, BOX otherwise
-      const bool q1 = (d.prm.quirks & 2) != 0;
-      for (int k = 0; k < 3; k++) {
-        const bool contact = c >= nj;
-        lo[3 * c + k] = (contact && !q1 && k < 2) ? -1.0 : 0.0;
-        hi[3 * c + k] = (contact && !q1 && k < 2) ? 1.0 : __longlong_as_double(0x7ff0000000000000LL);   // +inf
-      }
-    }
-    __syncthreads();
-
-    // ---- 2. A = J M^-1 J^T (ensembles.cc:510): block (c, c') = sum over shared bodies ----
-    for (int e = tid; e < nc * nc; e += DT) {
-      const int c = e / nc, c2 = e % nc;
-      const int a0 = ci0[c], a1 = ci1[c], e0 = ci0[c2], e1 = ci1[c2];
-      double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      // visit the bodies of c in ascending column order, as the dense product does
-      for (int pass = 0; pass < 2; pass++) {
-        const int side = ((a0 <= a1) == (pass == 0)) ? 0 : 1;
-        const int bd = side ? a1 : a0;
-        if (bd < 0) continue;
-        int side2 = -1;
-        if (bd == e0) side2 = 0; else if (bd == e1) side2 = 1;
-        if (side2 < 0) continue;
-        const double* Bx = Jb + (size_t)c * 72 + 36 + 18 * side;
-        const double* Jy = Jb + (size_t)c2 * 72 + 18 * side2;
-        for (int k = 0; k < 3; k++)
-          for (int l = 0; l < 3; l++) {
-            double s2 = blk[3 * k + l];
-            for (int q = 0; q < 6; q++) s2 += Bx[6 * k + q] * Jy[6 * l + q];
-            blk[3 * k + l] = s2;
-          }
-      }
-      for (int k = 0; k < 3; k++)
-        for (int l = 0; l < 3; l++) A[(size_t)(3 * c + k) * R + 3 * c2 + l] = blk[3 * k + l];
-    }
-    __syncthreads();
-
-    // ---- 3. cfm decision (ensembles.cc:513-521) ----
-    bool good;
-    if (d.prm.cfm_mode == 1) good = false;
-    else if (d.prm.cfm_mode == 2) good = true;
-    else {
-      for (int e = tid; e < R * R; e += DT) F[e] = A[e];
-      __syncthreads();
-      good = well_conditioned(F, R, R);
-      __syncthreads();
-    }
-    if (!good) {
-      for (int i = tid; i < R; i += DT) A[(size_t)i * R + i] += d.prm.cfm;
-      cfm_applied = 1;
-      __syncthreads();
-    }
-
-    // ---- 4. Schur complement on the equality rows (lcp.cc:286-294); rows 0..E-1 are the joints ----
-    if (I > 0) {
-      if (E > 0) {
-        for (int e = tid; e < E * E; e += DT) F[(size_t)(e / E) * E + e % E] = A[(size_t)(e / E) * R + e % E];
-        __syncthreads();
-        ldlt_compute(F, E, E, tr, tmp);
-        // X[:, j] = A_ee^-1 A_ei[:, j] (j < I), X[:, I] = A_ee^-1 b_e ; all right-hand sides at once
-        for (int e = tid; e < E * (I + 1); e += DT) {
-          const int i = e / (I + 1), j = e % (I + 1);
-          X[e] = (j < I) ? A[(size_t)i * R + E + j] : b[i];
-        }
-        __syncthreads();
-        ldlt_solve_columns(F, E, E, tr, X, I + 1, I + 1);
-      }
-      for (int e = tid; e < I * (I + 1); e += DT) {
-        const int i = e / (I + 1), j = e % (I + 1);
-        double s2 = 0;
-        for (int k = 0; k < E; k++) s2 += A[(size_t)(E + i) * R + k] * X[(size_t)k * (I + 1) + j];
-        if (j < I) L[(size_t)i * I + j] = A[(size_t)(E + i) * R + E + j] - s2;
-        else rhsL[i] = b[E + i] - s2;
-      }
-      __syncthreads();
-
-      // ---- 5. Murty principal pivoting on (L, rhsL) with bounds lo/hi of the inequality rows ----
-      const double* loI = lo + E;
-      const double* hiI = hi + E;
-      for (int i = tid; i < I; i += DT) { S[i] = 1; x[i] = 0.0; wv[i] = -rhsL[i]; Cx[i] = loI[i]; bx[i] = 0.0; bw[i] = -rhsL[i]; }
-      __syncthreads();
-      const int max_it = (I >= 10) ? 1000 : (1 << I);
-      int iter = 0;
-      while (iter < max_it) {
-        if (check_murty(L, I, I, rhsL, x, wv, S, Cx, loI, hiI, 0.0, tmp)) break;
-        // gather the basic set
-        if (tid == 0) {
-          int ks = 0;
-          for (int i = 0; i < I; i++) if (S[i]) sidx[ks++] = i;
-          s_flag = ks;
-        }
-        __syncthreads();
-        const int ks = s_flag;
-        for (int e = tid; e < ks * ks; e += DT) F[e] = L[(size_t)sidx[e / ks] * I + sidx[e % ks]];
-        for (int i = tid; i < ks; i += DT) xs[i] = rhsL[sidx[i]];
-        __syncthreads();
-        ldlt_compute(F, ks, ks, tr, tmp);
-        ldlt_solve(F, ks, ks, tr, xs);
-        for (int i = tid; i < ks; i += DT) x[sidx[i]] = xs[i];
-        for (int i = tid; i < I; i += DT)
-          if (!S[i]) x[i] = (Cx[i] == loI[i]) ? loI[i] : hiI[i];
-        __syncthreads();
-        for (int i = tid; i < I; i += DT) {
-          if (S[i]) { wv[i] = 0.0; continue; }
-          double s2 = 0;
-          for (int k = 0; k < ks; k++) s2 += L[(size_t)i * I + sidx[k]] * xs[k];
-          wv[i] = s2 - rhsL[i];
-        }
-        __syncthreads();
-        // UpdatePreviousBestSolution (lcp.cc:127-137)
-        if (tid == 0) {
-          bool same = true;
-          double gn = 0, gp = 0, gnw = 0, gpw = 0;
-          for (int i = 0; i < I; i++) {
-            if (x[i] != bx[i] || wv[i] != bw[i]) same = false;
-            gn += (x[i] > 0) ? 0.0 : x[i];
-            gp += (bx[i] > 0) ? 0.0 : bx[i];
-          }
-          for (int i = 0; i < I; i++) { gnw += (wv[i] > 0) ? 0.0 : wv[i]; gpw += (bw[i] > 0) ? 0.0 : bw[i]; }
-          s_flag = (!same && (gn + gnw) > (gp + gpw)) ? 1 : 0;
-        }
-        __syncthreads();
-        if (s_flag)
-          for (int i = tid; i < I; i += DT) { bx[i] = x[i]; bw[i] = wv[i]; }
-        __syncthreads();
-        ++iter;
-      }
-      pivots = iter;
-      for (int i = tid; i < I; i += DT) { x[i] = bx[i]; wv[i] = bw[i]; }
-      __syncthreads();
-      const int ok = check_murty(L, I, I, rhsL, x, wv, S, Cx, loI, hiI, (iter >= max_it) ? 1e-8 : 0.0, tmp);
-      if (!ok) lcp_failed = 1;
-    }
-
-    // ---- 6. x_e = A_ee.ldlt().solve(b_e - A_ei x_i)  (lcp.cc:317) ----
-    if (E > 0) {
-      for (int i = tid; i < E; i += DT) {
-        double s2 = 0;
-        for (int j = 0; j < I; j++) s2 += A[(size_t)i * R + E + j] * x[j];
-        xs[i] = b[i] - s2;
-      }
-      __syncthreads();
-      // (F was reused by Murty: refactor A_ee)
-      for (int e = tid; e < E * E; e += DT) F[(size_t)(e / E) * E + e % E] = A[(size_t)(e / E) * R + e % E];
-      __syncthreads();
-      ldlt_compute(F, E, E, tr, tmp);
-      ldlt_solve(F, E, E, tr, xs);
-      for (int i = tid; i < E; i += DT) lamv[i] = xs[i];
-    }
-    for (int i = tid; i < I; i += DT) lamv[E + i] = x[i];
-    __syncthreads();
-
-    // ---- 7. outputs + a = M^-1 J^T lambda (per body, constraints in reference order) ----
-    for (int i = tid; i < R; i += DT) {
-      lam_out[i] = lamv[i];
-      rs_out[i] = (i < E) ? 3 : (S[i - E] ? 0 : 1);
-    }
-    for (int bd = tid; bd < n; bd += DT) {
-      double g[6] = {0, 0, 0, 0, 0, 0};
-      for (int c = 0; c < nc; c++) {
-        for (int side = 0; side < 2; side++) {
-          if ((side ? ci1[c] : ci0[c]) != bd) continue;
-          const double* Jx = Jb + (size_t)c * 72 + 18 * side;
-          for (int k = 0; k < 3; k++) {
-            const double l = lamv[3 * c + k];
-            for (int q = 0; q < 6; q++) g[q] += Jx[6 * k + q] * l;
-          }
-        }
-      }
-      const double mi = st[bd];
-      double Ii[9];
-      for (int q = 0; q < 9; q++) Ii[q] = st[(1 + q) * n + bd];
-      d3 al = mk3(g[0], g[1], g[2]) * mi;
-      d3 aa = mmulv(Ii, mk3(g[3], g[4], g[5]));
-      sa[bd] = al.x; sa[n + bd] = al.y; sa[2 * n + bd] = al.z;
-      sa[3 * n + bd] = aa.x; sa[4 * n + bd] = aa.y; sa[5 * n + bd] = aa.z;
-    }
+// lcp.cc:98-104: sum of the non-positive parts of v in index order; exact zeros and positive
+// entries contribute +0 and are skipped (the sum starts at +0 and can never become -0).
+__device__ double ordered_nonpositive_sum(const double* v, int len, unsigned short* list, unsigned char* flag) {
+  for (int i = threadIdx.x; i < len; i += DT) flag[i] = (v[i] < 0) ? 1 : 0;
+  __syncthreads();
+  const int cnt = build_index_list(flag, 1, len, list);
+  __shared__ double s_sum;
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int q = 0; q < cnt; q++) s += v[list[q]];
+    s_sum = s;
   }
   __syncthreads();
+  const double r = s_sum;
+  __syncthreads();
+  return r;
+}
 
-  if (tid == 0) {
-    stt[4] = 0;
-    stt[5] = pivots;
-    stt[6] = cfm_applied;
-    stt[7] = 0;
-    d.resid[w] = 0.0;
-    int flags = d.status[w] & ~1;
-    if (lcp_failed) flags |= 1;
-    if (overflow) flags |= 32;
-    d.status[w] = flags;
-  }
-
-  // ---- 8. integrate (same arithmetic as the PGS path) ----
+// ---- integrate (same arithmetic as the PGS path): v' = v + dt (M^-1 f + a), midpoint position ---
+__device__ void integrate_world(const EggDev& d, int w, double dt, const double* sa) {
+  const int n = d.n;
+  const double* st = d.stat + (size_t)w * EGG_STAT * n;
   double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
-  for (int bd = tid; bd < n; bd += DT) {
+  for (int bd = threadIdx.x; bd < n; bd += DT) {
     const double mi = st[bd];
     double Ii[9];
     for (int k = 0; k < 9; k++) Ii[k] = st[(1 + k) * n + bd];
@@ -545,40 +522,11 @@ __global__ void __launch_bounds__(DT) egg_dense_kernel(EggDev d, double dt, doub
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Position relaxation: one iteration of Ensemble::InitStabilize's loop body
-// (/root/reference/eggshell/ensembles.cc:602-622): StepPositionRelaxation(dt = 0.5) =
-// StepPositions_ExplicitEuler(dt, -0.2 J^T (J J^T)^-1 err)  (:647-650, 659-666, 553-561) for every
-// world whose squared position error still exceeds 1e-9 and whose step counter is below
-// max_steps.  Contacts must have been refreshed WITHOUT de-duplication (the reference only runs
-// CheckAndCorrectEnsembleState after the loop) and the records assembled for the current state.
-// prog[w] = {steps taken, active flag}; err2[w] = squared error seen by this call.
-__global__ void __launch_bounds__(DT) egg_relax_kernel(EggDev d, double dt, double step_scale, int max_steps, double* scratch,
-                                                        size_t per_world, int Rcap, int* prog, double* err2, int* any_active) {
-  const int w = blockIdx.x, tid = threadIdx.x, n = d.n, nj = d.nj;
-  const int nc = nj + d.c_count[w];
-  const int R = 3 * nc;
-  __shared__ double s_e2;
-  __shared__ int s_go;
-  double* base = scratch + (size_t)w * per_world;
-  double* A = base;
-  double* F = A + (size_t)Rcap * Rcap * 2;
-  double* Jb = F + (size_t)Rcap * Rcap + (size_t)Rcap * (Rcap + 1);
-  double* vec = Jb + (size_t)(Rcap / 3 + 1) * 72;
-  double* e = vec;                 // err [R], reference row order
-  double* y = vec + Rcap;
-  double* tmp = vec + 2 * Rcap;
-  int* ivec = reinterpret_cast<int*>(base + per_world) - 4 * Rcap;
-  int* tr = ivec;
-  int* ci0 = ivec + 2 * Rcap;
-  int* ci1 = ivec + 3 * Rcap;
-  const double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+// Jacobian blocks J0, J1 (3x6 each) of every constraint in REFERENCE order from the per-world
+// records (which are in level order); zero_world: write zeros on the world / ground side.
+__device__ void jacobian_blocks(const EggDev& d, int w, int nc, double* Jb, int* ci0, int* ci1, double* rhs_out, bool zero_world) {
   const double* recs = d.rec + (size_t)w * d.nrec * EGG_REC;
-  const double* geom = d.c_geom + (size_t)w * 7 * d.maxc;
-  const bool fits = R <= Rcap;
-
-  // J blocks + position error per constraint, reference order
-  for (int s = tid; fits && s < nc; s += DT) {
+  for (int s = threadIdx.x; s < nc; s += DT) {
     const double* r = recs + (size_t)s * EGG_REC;
     const int i0 = __double2loint(r[REC_IDX]), i1 = __double2hiint(r[REC_IDX]);
     const int c = __double2loint(r[REC_META]);
@@ -586,130 +534,591 @@ __global__ void __launch_bounds__(DT) egg_relax_kernel(EggDev d, double dt, doub
     d3 r0 = mk3(r[REC_R0], r[REC_R0 + 1], r[REC_R0 + 2]), r1 = mk3(r[REC_R1], r[REC_R1 + 1], r[REC_R1 + 2]);
     double* J0 = Jb + (size_t)c * 72;
     double* J1 = J0 + 18;
+    const double z0 = (zero_world && i0 < 0) ? 0.0 : 1.0, z1 = (zero_world && i1 < 0) ? 0.0 : 1.0;
     for (int k = 0; k < 3; k++) {
       d3 rc = mk3(r[REC_RC + 3 * k], r[REC_RC + 3 * k + 1], r[REC_RC + 3 * k + 2]);
       d3 a0 = cross3(rc, r0), a1 = cross3(r1, rc);
-      const double z0 = (i0 >= 0) ? 1.0 : 0.0, z1 = (i1 >= 0) ? 1.0 : 0.0;
       J0[6 * k] = -rc.x * z0; J0[6 * k + 1] = -rc.y * z0; J0[6 * k + 2] = -rc.z * z0; J0[6 * k + 3] = a0.x * z0; J0[6 * k + 4] = a0.y * z0; J0[6 * k + 5] = a0.z * z0;
       J1[6 * k] = rc.x * z1; J1[6 * k + 1] = rc.y * z1; J1[6 * k + 2] = rc.z * z1; J1[6 * k + 3] = a1.x * z1; J1[6 * k + 4] = a1.y * z1; J1[6 * k + 5] = a1.z * z1;
-    }
-    if (c < nj) {                                            // joints.cc:3-11
-      d3 p0 = mk3(dyn[i0], dyn[n + i0], dyn[2 * n + i0]);
-      d3 er;
-      if (i1 < 0) {
-        const double* jc = d.jc + (size_t)w * 6 * nj;
-        er = p0 + r0 - mk3(jc[3 * nj + c], jc[4 * nj + c], jc[5 * nj + c]);
-      } else {
-        er = p0 + r0 - mk3(dyn[i1], dyn[n + i1], dyn[2 * n + i1]) - r1;
-      }
-      e[3 * c] = er.x; e[3 * c + 1] = er.y; e[3 * c + 2] = er.z;
-    } else {                                                 // contact.cc:14-22
-      e[3 * c] = 0.0; e[3 * c + 1] = 0.0; e[3 * c + 2] = -geom[6 * d.maxc + (c - nj)];
+      if (rhs_out) rhs_out[3 * c + k] = r[REC_RHS + k];
     }
   }
-  __syncthreads();
-  if (tid == 0) {
-    double s2 = 0;
-    for (int i = 0; fits && i < R; i++) s2 += e[i] * e[i];
-    s_e2 = s2;
-    const int steps = prog[2 * w];
-    s_go = (fits && s2 > 1e-9 && steps < max_steps) ? 1 : 0;
-    err2[w] = s2;
-    prog[2 * w + 1] = s_go;
-    if (s_go) { prog[2 * w] = steps + 1; atomicOr(any_active, 1); }
-    if (!fits) atomicOr(&d.status[w], 32 /*EGG_ST_DENSE_OVERFLOW*/);
-  }
-  __syncthreads();
-  if (!s_go) return;
+}
 
-  // A = J J^T (ensembles.cc:664), blocks over shared bodies in ascending body order
-  for (int q = tid; q < nc * nc; q += DT) {
-    const int c = q / nc, c2 = q % nc;
-    const int a0 = ci0[c], a1 = ci1[c], e0 = ci0[c2], e1 = ci1[c2];
-    double blk[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int pass = 0; pass < 2; pass++) {
-      const int side = ((a0 <= a1) == (pass == 0)) ? 0 : 1;
-      const int bd = side ? a1 : a0;
-      if (bd < 0) continue;
-      int side2 = -1;
-      if (bd == e0) side2 = 0; else if (bd == e1) side2 = 1;
-      if (side2 < 0) continue;
-      const double* Jx = Jb + (size_t)c * 72 + 18 * side;
-      const double* Jy = Jb + (size_t)c2 * 72 + 18 * side2;
-      for (int k = 0; k < 3; k++)
-        for (int l = 0; l < 3; l++) {
-          double s2 = blk[3 * k + l];
-          for (int t = 0; t < 6; t++) s2 += Jx[6 * k + t] * Jy[6 * l + t];
-          blk[3 * k + l] = s2;
-        }
-    }
+// Block (c, c2) of G = X J^T with X = J M^-1 (use_minv) or X = J: sum over the shared bodies in
+// ascending column (= body) order, as the dense products of the oracle do.
+__device__ __forceinline__ void pair_block(const double* Jb, const int* ci0, const int* ci1, int c, int c2, bool use_minv, double* blk) {
+  const int a0 = ci0[c], a1 = ci1[c], e0 = ci0[c2], e1 = ci1[c2];
+  for (int q = 0; q < 9; q++) blk[q] = 0.0;
+  for (int pass = 0; pass < 2; pass++) {
+    const int side = ((a0 <= a1) == (pass == 0)) ? 0 : 1;
+    const int bd = side ? a1 : a0;
+    if (bd < 0) continue;
+    int side2 = -1;
+    if (bd == e0) side2 = 0; else if (bd == e1) side2 = 1;
+    if (side2 < 0) continue;
+    const double* Bx = Jb + (size_t)c * 72 + (use_minv ? 36 : 0) + 18 * side;
+    const double* Jy = Jb + (size_t)c2 * 72 + 18 * side2;
     for (int k = 0; k < 3; k++)
-      for (int l = 0; l < 3; l++) A[(size_t)(3 * c + k) * R + 3 * c2 + l] = blk[3 * k + l];
-  }
-  for (int i = tid; i < R; i += DT) y[i] = e[i];
-  __syncthreads();
-  ldlt_compute(A, R, R, tr, tmp);
-  ldlt_solve(A, R, R, tr, y);
-
-  // velocity_correction = -step_scale J^T y ; StepPositions_ExplicitEuler(dt, .)
-  double* dynw = d.dyn + (size_t)w * EGG_DYN * n;
-  for (int bd = tid; bd < n; bd += DT) {
-    double g[6] = {0, 0, 0, 0, 0, 0};
-    for (int c = 0; c < nc; c++)
-      for (int side = 0; side < 2; side++) {
-        if ((side ? ci1[c] : ci0[c]) != bd) continue;
-        const double* Jx = Jb + (size_t)c * 72 + 18 * side;
-        for (int k = 0; k < 3; k++)
-          for (int t = 0; t < 6; t++) g[t] += (-1.0 * step_scale * Jx[6 * k + t]) * y[3 * c + k];
+      for (int l = 0; l < 3; l++) {
+        double s2 = blk[3 * k + l];
+        for (int q = 0; q < 6; q++) s2 += Bx[6 * k + q] * Jy[6 * l + q];
+        blk[3 * k + l] = s2;
       }
-    d3 p = mk3(dynw[bd], dynw[n + bd], dynw[2 * n + bd]) + dt * mk3(g[0], g[1], g[2]);
-    d3 wv = mk3(g[3], g[4], g[5]);
-    double z2 = dot3(wv, wv);
-    d3 axis = (z2 > 0) ? wv / sqrt(z2) : wv;
-    double ha = 0.5 * (norm3(wv) * dt);
-    double qw = cos(ha), sn = sin(ha);
-    double qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
-    double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
-    double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-    double Q[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
-    double Rm[9], Rn[9];
-    for (int k = 0; k < 9; k++) Rm[k] = dynw[(3 + k) * n + bd];
-    mmulm(Q, Rm, Rn);
-    dynw[bd] = p.x; dynw[n + bd] = p.y; dynw[2 * n + bd] = p.z;
-    for (int k = 0; k < 9; k++) dynw[(3 + k) * n + bd] = Rn[k];
   }
+}
+__device__ __forceinline__ bool shares_body(const int* ci0, const int* ci1, int c, int c2) {
+  const int a0 = ci0[c], a1 = ci1[c], e0 = ci0[c2], e1 = ci1[c2];
+  return (a0 >= 0 && (a0 == e0 || a0 == e1)) || (a1 >= 0 && (a1 == e0 || a1 == e1));
+}
+
+// ---- the step kernel ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, double* scratch, DenseCfg cfg) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int tid = threadIdx.x, n = d.n, nj = d.nj;
+  const Sm sm = carve(sm_raw, cfg, n);
+  __shared__ int s_world, s_flag;
+  __shared__ double s_red[NWARP];
+  double* slab = scratch + (size_t)blockIdx.x * cfg.per_cta;
+  double* A = slab + cfg.off_A;
+  double* Wk = slab + cfg.off_Wk;
+  double* Lm = slab + cfg.off_Lm;
+  double* T1 = slab + cfg.off_T1;
+  double* Fg = slab + cfg.off_Fg;
+  double* Jb = slab + cfg.off_Jb;
+  double* b = slab + cfg.off_vec;                 // rhs [R]
+  double* lamv = b + cfg.Rcap;                    // lambda [R], reference row order
+  int* ci0 = reinterpret_cast<int*>(slab + cfg.off_int);
+  int* ci1 = ci0 + cfg.ncap;
+  unsigned short* piv = reinterpret_cast<unsigned short*>(ci1 + cfg.ncap);   // [Rcap]
+  const bool boxed = (d.prm.quirks & 2) == 0;     // q1 off: BOX friction bounds honoured
+
+  while (true) {
+    if (tid == 0) s_world = atomicAdd(d.work_ctr + 1, 1);
+    __syncthreads();
+    const int w = s_world;
+    __syncthreads();
+    if (w >= d.W) break;
+
+    const int nc = nj + d.c_count[w];
+    int R = 3 * nc;
+    const int E = 3 * nj;
+    const double* st = d.stat + (size_t)w * EGG_STAT * n;
+    double* lam_out = d.lam_out + (size_t)w * 3 * d.nrec;
+    int* rs_out = d.row_state + (size_t)w * 3 * d.nrec;
+    int* stt = d.stats + (size_t)w * 8;
+    for (int i = tid; i < 6 * n; i += DT) sm.sa[i] = 0.0;
+    bool overflow = false;
+    if (R > cfg.Rcap) { overflow = true; R = 0; }
+    const int I = R - (R ? E : 0);
+    int pivots = 0, cfm_applied = 0, lcp_failed = 0;
+    // FP64 operations of the reference algorithm on this world (mul and add counted separately):
+    // A = J M^-1 J^T is not counted (sparse, O(rows)); cfm decision = one factorisation R^3/3;
+    // A_ee^-1 by LU 2 E^3; Schur products 2 (I E^2 + I^2 E) as dense GEMMs; per pivot LDL^T k^3/3 +
+    // two triangular solves 2 k^2 + w = A_NS x_S 2 k (I - k); final A_ee LDL^T + solve.
+    double work = 0.0;
+
+    if (R > 0) {
+      // ---- 1. Jacobian blocks, J M^-1 blocks and rhs in reference row order ----
+      jacobian_blocks(d, w, nc, Jb, ci0, ci1, b, false);
+      __syncthreads();
+      for (int c = tid; c < nc; c += DT) {
+        for (int side = 0; side < 2; side++) {
+          const int bd = side ? ci1[c] : ci0[c];
+          const double* Jx = Jb + (size_t)c * 72 + 18 * side;
+          double* Bx = Jb + (size_t)c * 72 + 36 + 18 * side;
+          if (bd < 0) { for (int q = 0; q < 18; q++) Bx[q] = 0.0; continue; }
+          const double mi = st[bd];
+          double Ii[9];
+          for (int q = 0; q < 9; q++) Ii[q] = st[(1 + q) * n + bd];
+          for (int k = 0; k < 3; k++) {       // (J * M^-1) row k
+            for (int q = 0; q < 3; q++) Bx[6 * k + q] = Jx[6 * k + q] * mi;
+            for (int q = 0; q < 3; q++) {
+              double s2 = 0;
+              for (int t = 0; t < 3; t++) s2 += Jx[6 * k + 3 + t] * Ii[3 * t + q];
+              Bx[6 * k + 3 + q] = s2;
+            }
+          }
+        }
+      }
+      __syncthreads();
+
+      // ---- 2. A = J M^-1 J^T (ensembles.cc:510) ----
+      for (int e = tid; e < nc * nc; e += DT) {
+        const int c = e / nc, c2 = e % nc;
+        double blk[9];
+        pair_block(Jb, ci0, ci1, c, c2, true, blk);
+        for (int k = 0; k < 3; k++)
+          for (int l = 0; l < 3; l++) A[(size_t)(3 * c + k) * R + 3 * c2 + l] = blk[3 * k + l];
+      }
+      __syncthreads();
+
+      // ---- 3. cfm decision (ensembles.cc:513-521) ----
+      bool good;
+      if (d.prm.cfm_mode == 1) good = false;
+      else if (d.prm.cfm_mode == 2) good = true;
+      else {
+        for (int e = tid; e < R * R; e += DT) Wk[e] = A[e];
+        __syncthreads();
+        work += (double)R * R * R / 3.0;
+        double lb = 0;
+        good = pivoted_ldlt_range(Wk, R, piv, &lb) != 0;
+        __syncthreads();
+        if (good && lb >= 1e4) good = cond_refine_is_good(A, Wk, R, piv, sm.x, sm.w, sm.xs, s_red);
+        __syncthreads();
+      }
+      if (!good) {
+        for (int i = tid; i < R; i += DT) A[(size_t)i * R + i] += d.prm.cfm;
+        cfm_applied = 1;
+        __syncthreads();
+      }
+
+      // ---- 4. Schur complement on the equality rows (lcp.cc:286-294); rows 0..E-1 are the joints ----
+      if (I > 0) {
+        if (E > 0) {
+          // 4a. A_ee^-1 by partial-pivot LU (orc::lu_inverse): lu in Wk[0 .. E^2), inverse in Wk[E^2 .. 2 E^2)
+          work += 2.0 * E * E * E + 2.0 * ((double)I * E * E + (double)I * I * E);
+          double* lu = ((size_t)E * E <= (size_t)cfg.Fcap) ? sm.F : Wk;     // the LU lives in shared memory when it fits
+          double* Ainv = Wk + (size_t)E * E;
+          unsigned short* lperm = sm.sidx;           // row permutation of the LU (free until the Murty loop)
+          for (int e = tid; e < E * E; e += DT) lu[e] = A[(size_t)(e / E) * R + e % E];
+          for (int i = tid; i < E; i += DT) lperm[i] = (unsigned short)i;
+          __syncthreads();
+          for (int k = 0; k < E; k++) {
+            // pivot: first row i >= k with the largest |lu(i,k)|
+            __shared__ double s_pv[NWARP];
+            __shared__ int s_pi[NWARP];
+            double best = -1.0;
+            int bi = E;
+            for (int i = k + tid; i < E; i += DT) { const double v = fabs(lu[(size_t)i * E + k]); if (v > best) { best = v; bi = i; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double ob = __shfl_xor_sync(FULL, best, o);
+              const int oi = __shfl_xor_sync(FULL, bi, o);
+              if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if ((tid & 31) == 0) { s_pv[tid >> 5] = best; s_pi[tid >> 5] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+              double bb = s_pv[0]; int ix = s_pi[0];
+              for (int q = 1; q < NWARP; q++) if (s_pv[q] > bb || (s_pv[q] == bb && s_pi[q] < ix)) { bb = s_pv[q]; ix = s_pi[q]; }
+              s_flag = ix;
+            }
+            __syncthreads();
+            const int pv = s_flag;
+            if (pv != k) {
+              for (int j = tid; j < E; j += DT) { const double t = lu[(size_t)k * E + j]; lu[(size_t)k * E + j] = lu[(size_t)pv * E + j]; lu[(size_t)pv * E + j] = t; }
+              if (tid == 0) { const unsigned short t = lperm[k]; lperm[k] = lperm[pv]; lperm[pv] = t; }
+              __syncthreads();
+            }
+            const double dd = lu[(size_t)k * E + k];
+            if (dd != 0) {
+              for (int i = k + 1 + tid; i < E; i += DT) lu[(size_t)i * E + k] /= dd;
+              __syncthreads();
+            }
+            // trailing update: thread per column j (coalesced), multiplier column broadcast
+            for (int j = k + 1 + tid; j < E; j += DT) {
+              const double ukj = lu[(size_t)k * E + j];
+              for (int i = k + 1; i < E; i++) {
+                const double l = lu[(size_t)i * E + k];
+                if (l == 0) continue;
+                lu[(size_t)i * E + j] -= l * ukj;
+              }
+            }
+            __syncthreads();
+          }
+          // inverse, one thread per column c; the column lives in Ainv(:, c) (coalesced over the threads)
+          for (int c = tid; c < E; c += DT) {
+            for (int i = 0; i < E; i++) {
+              double s = (lperm[i] == c) ? 1.0 : 0.0;
+              for (int j = 0; j < i; j++) s -= lu[(size_t)i * E + j] * Ainv[(size_t)j * E + c];
+              Ainv[(size_t)i * E + c] = s;
+            }
+            for (int i = E - 1; i >= 0; i--) {
+              double s = Ainv[(size_t)i * E + c];
+              for (int j = i + 1; j < E; j++) s -= lu[(size_t)i * E + j] * Ainv[(size_t)j * E + c];
+              Ainv[(size_t)i * E + c] = s / lu[(size_t)i * E + i];
+            }
+          }
+          __syncthreads();
+          // 4b. T1 = A_ie A_ee^-1  (I x E); only joints that share a body with the contact of row i
+          //     have non-zero entries in A_ie (zero entries are skipped by the oracle's matmul as well)
+          for (int e = tid; e < I * E; e += DT) {
+            const int i = e / E, j = e % E;
+            const int c = nj + i / 3;
+            double s = 0;
+            for (int q = 0; q < nj; q++) {
+              if (!shares_body(ci0, ci1, c, q)) continue;
+              for (int t = 0; t < 3; t++) {
+                const int k = 3 * q + t;
+                const double aik = A[(size_t)(E + i) * R + k];
+                if (aik == 0) continue;
+                s += aik * Ainv[(size_t)k * E + j];
+              }
+            }
+            T1[e] = s;
+          }
+          __syncthreads();
+          // 4c. lhs = A_ii - T1 A_ei ; rhs = b_i - T1 b_e
+          for (int e = tid; e < I * (I + 1); e += DT) {
+            const int i = e / (I + 1), j = e % (I + 1);
+            double s = 0;
+            if (j < I) {
+              const int c2 = nj + j / 3;
+              for (int q = 0; q < nj; q++) {
+                if (!shares_body(ci0, ci1, c2, q)) continue;       // A_ei(3q.., j) structurally zero otherwise
+                for (int t = 0; t < 3; t++) {
+                  const int k = 3 * q + t;
+                  const double aik = T1[(size_t)i * E + k];
+                  if (aik == 0) continue;
+                  s += aik * A[(size_t)k * R + E + j];
+                }
+              }
+              Lm[(size_t)i * I + j] = A[(size_t)(E + i) * R + E + j] - s;
+            } else {
+              for (int k = 0; k < E; k++) s += T1[(size_t)i * E + k] * b[k];
+              sm.rhs[i] = b[E + i] - s;
+            }
+          }
+        } else {
+          for (int e = tid; e < I * I; e += DT) Lm[e] = A[e];
+          for (int i = tid; i < I; i += DT) sm.rhs[i] = b[i];
+        }
+        __syncthreads();
+
+        // ---- 5. Murty principal pivoting on (Lm, rhs) ----
+        for (int i = tid; i < I; i += DT) { sm.S[i] = 1; sm.athi[i] = 0; sm.x[i] = 0.0; sm.w[i] = -sm.rhs[i]; sm.bx[i] = 0.0; sm.bw[i] = -sm.rhs[i]; }
+        __syncthreads();
+        // goodness of the best-so-far pair (lcp.cc:98-104), kept instead of recomputed
+        double gbest = ordered_nonpositive_sum(sm.bx, I, sm.perm, reinterpret_cast<unsigned char*>(sm.tmp));
+        gbest = gbest + ordered_nonpositive_sum(sm.bw, I, sm.perm, reinterpret_cast<unsigned char*>(sm.tmp));
+        const int max_it = (I >= 10) ? 1000 : (1 << I);
+        int iter = 0;
+        while (iter < max_it) {
+          if (check_murty(Lm, I, sm, sm.x, sm.w, boxed, 0.0)) break;
+          const int ks = build_index_list(sm.S, 1, I, sm.sidx);
+          work += (double)ks * ks * ks / 3.0 + 2.0 * ks * ks + 2.0 * ks * (double)(I - ks);
+          if (ks > 0) {
+            double* F = ldlt_block(Lm, I, sm.sidx, ks, sm, cfg, Fg);
+            for (int p = tid; p < ks; p += DT) sm.xs[p] = sm.rhs[sm.sidx[sm.perm[p]]];
+            __syncthreads();
+            ldlt_solve(F, ks, sm.xs);
+            for (int p = tid; p < ks; p += DT) sm.x[sm.sidx[sm.perm[p]]] = sm.xs[p];
+          }
+          for (int i = tid; i < I; i += DT)
+            if (!sm.S[i]) sm.x[i] = sm.athi[i] ? row_hi(i, boxed) : row_lo(i, boxed);
+          __syncthreads();
+          for (int i = tid; i < I; i += DT) {
+            if (sm.S[i]) { sm.w[i] = 0.0; continue; }
+            const double* Li = Lm + (size_t)i * I;
+            double s2 = 0;
+            for (int k = 0; k < ks; k++) { const int g = sm.sidx[k]; s2 += Li[g] * sm.x[g]; }
+            sm.w[i] = s2 - sm.rhs[i];
+          }
+          __syncthreads();
+          // UpdatePreviousBestSolution (lcp.cc:127-137)
+          int differs = 0;
+          for (int i = tid; i < I; i += DT) differs |= (sm.x[i] != sm.bx[i]) || (sm.w[i] != sm.bw[i]);
+          if (__syncthreads_or(differs)) {
+            double g = ordered_nonpositive_sum(sm.x, I, sm.perm, reinterpret_cast<unsigned char*>(sm.tmp));
+            g = g + ordered_nonpositive_sum(sm.w, I, sm.perm, reinterpret_cast<unsigned char*>(sm.tmp));
+            if (g > gbest) {
+              gbest = g;
+              for (int i = tid; i < I; i += DT) { sm.bx[i] = sm.x[i]; sm.bw[i] = sm.w[i]; }
+            }
+            __syncthreads();
+          }
+          ++iter;
+        }
+        pivots = iter;
+        for (int i = tid; i < I; i += DT) { sm.x[i] = sm.bx[i]; sm.w[i] = sm.bw[i]; }
+        __syncthreads();
+        if (!check_murty(Lm, I, sm, sm.x, sm.w, boxed, (iter >= max_it) ? 1e-8 : 0.0)) lcp_failed = 1;
+      }
+
+      // ---- 6. x_e = A_ee.ldlt().solve(b_e - A_ei x_i)  (lcp.cc:317) ----
+      if (E > 0) {
+        for (int i = tid; i < E; i += DT) {
+          double s2 = 0;
+          for (int j = 0; j < I; j++) s2 += A[(size_t)i * R + E + j] * sm.x[j];
+          sm.w[i] = b[i] - s2;                 // (w is free now)
+        }
+        __syncthreads();
+        work += (double)E * E * E / 3.0 + 2.0 * E * E + 2.0 * E * I;
+        double* F = ldlt_block(A, R, nullptr, E, sm, cfg, Fg);
+        for (int p = tid; p < E; p += DT) sm.xs[p] = sm.w[sm.perm[p]];
+        __syncthreads();
+        ldlt_solve(F, E, sm.xs);
+        for (int p = tid; p < E; p += DT) lamv[sm.perm[p]] = sm.xs[p];
+      }
+      for (int i = tid; i < I; i += DT) lamv[E + i] = sm.x[i];
+      __syncthreads();
+
+      // ---- 7. outputs + a = M^-1 J^T lambda (per body, constraints in reference order) ----
+      for (int i = tid; i < R; i += DT) {
+        lam_out[i] = lamv[i];
+        rs_out[i] = (i < E) ? 3 : (sm.S[i - E] ? 0 : 1);
+      }
+      for (int bd = tid; bd < n; bd += DT) {
+        double g[6] = {0, 0, 0, 0, 0, 0};
+        for (int c = 0; c < nc; c++) {
+          for (int side = 0; side < 2; side++) {
+            if ((side ? ci1[c] : ci0[c]) != bd) continue;
+            const double* Jx = Jb + (size_t)c * 72 + 18 * side;
+            for (int k = 0; k < 3; k++) {
+              const double l = lamv[3 * c + k];
+              for (int q = 0; q < 6; q++) g[q] += Jx[6 * k + q] * l;
+            }
+          }
+        }
+        const double mi = st[bd];
+        double Ii[9];
+        for (int q = 0; q < 9; q++) Ii[q] = st[(1 + q) * n + bd];
+        d3 al = mk3(g[0], g[1], g[2]) * mi;
+        d3 aa = mmulv(Ii, mk3(g[3], g[4], g[5]));
+        sm.sa[bd] = al.x; sm.sa[n + bd] = al.y; sm.sa[2 * n + bd] = al.z;
+        sm.sa[3 * n + bd] = aa.x; sm.sa[4 * n + bd] = aa.y; sm.sa[5 * n + bd] = aa.z;
+      }
+    }
+    __syncthreads();
+
+    if (tid == 0) {
+      stt[4] = 0;
+      stt[5] = pivots;
+      stt[6] = cfm_applied;
+      stt[7] = 0;
+      d.resid[w] = 0.0;
+      if (d.work) d.work[w] = work;
+      int flags = d.status[w] & ~1;
+      if (lcp_failed) flags |= 1;
+      if (overflow) flags |= 32;
+      d.status[w] = flags;
+    }
+    __syncthreads();
+    integrate_world(d, w, dt, sm.sa);
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Position relaxation.  One iteration of the loop body of Ensemble::InitStabilize
+// (ensembles.cc:602-622; mode 0: StepPositionRelaxation = StepPositions_ExplicitEuler(dt, c)) or of
+// Ensemble::PostStabilize (ensembles.cc:624-645; mode 1: StepPostStabilization = the same position
+// step plus v += c) with c = -step_scale J^T (J J^T)^-1 err (ensembles.cc:659-666), for every world
+// whose squared position error still exceeds 1e-9 and whose step counter is below max_steps.
+// The records must have been assembled for the current state (and, for mode 0, the contacts
+// refreshed WITHOUT de-duplication: the reference only runs CheckAndCorrectEnsembleState after the
+// loop).  prog[w] = {steps taken, active flag}; err2[w] = squared error seen by this call.
+__global__ void __launch_bounds__(DT, 2) egg_relax_kernel(EggDev d, double dt, double step_scale, int max_steps, int mode, double* scratch,
+                                                           DenseCfg cfg, int* prog, double* err2, int* any_active) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int tid = threadIdx.x, n = d.n, nj = d.nj;
+  const Sm sm = carve(sm_raw, cfg, n);
+  __shared__ int s_world, s_go;
+  double* slab = scratch + (size_t)blockIdx.x * cfg.per_cta;
+  double* A = slab + cfg.off_A;
+  double* Fg = slab + cfg.off_Fg;
+  double* Jb = slab + cfg.off_Jb;
+  int* ci0 = reinterpret_cast<int*>(slab + cfg.off_int);
+  int* ci1 = ci0 + cfg.ncap;
+  double* e = sm.x;                // err [R], reference row order
+
+  while (true) {
+    if (tid == 0) s_world = atomicAdd(d.work_ctr + 1, 1);
+    __syncthreads();
+    const int w = s_world;
+    __syncthreads();
+    if (w >= d.W) break;
+    const int nc = nj + d.c_count[w];
+    const int R = 3 * nc;
+    const bool fits = R <= cfg.Rcap;
+    const double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
+    const double* recs = d.rec + (size_t)w * d.nrec * EGG_REC;
+    const double* geom = d.c_geom + (size_t)w * 7 * d.maxc;
+
+    if (fits) jacobian_blocks(d, w, nc, Jb, ci0, ci1, nullptr, true);
+    __syncthreads();
+    // position error per constraint, reference order (joints.cc:3-11, contact.cc:14-22)
+    for (int s = tid; fits && s < nc; s += DT) {
+      const double* r = recs + (size_t)s * EGG_REC;
+      const int i0 = __double2loint(r[REC_IDX]), i1 = __double2hiint(r[REC_IDX]);
+      const int c = __double2loint(r[REC_META]);
+      if (c < nj) {
+        d3 r0 = mk3(r[REC_R0], r[REC_R0 + 1], r[REC_R0 + 2]), r1 = mk3(r[REC_R1], r[REC_R1 + 1], r[REC_R1 + 2]);
+        d3 p0 = mk3(dyn[i0], dyn[n + i0], dyn[2 * n + i0]);
+        d3 er;
+        if (i1 < 0) {
+          const double* jc = d.jc + (size_t)w * 6 * nj;
+          er = p0 + r0 - mk3(jc[3 * nj + c], jc[4 * nj + c], jc[5 * nj + c]);
+        } else {
+          er = p0 + r0 - mk3(dyn[i1], dyn[n + i1], dyn[2 * n + i1]) - r1;
+        }
+        e[3 * c] = er.x; e[3 * c + 1] = er.y; e[3 * c + 2] = er.z;
+      } else {
+        e[3 * c] = 0.0; e[3 * c + 1] = 0.0; e[3 * c + 2] = -geom[6 * d.maxc + (c - nj)];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double s2 = 0;
+      for (int i = 0; fits && i < R; i++) s2 += e[i] * e[i];
+      const int steps = prog[2 * w];
+      s_go = (fits && s2 > 1e-9 && steps < max_steps) ? 1 : 0;
+      err2[w] = s2;
+      prog[2 * w + 1] = s_go;
+      if (s_go) { prog[2 * w] = steps + 1; atomicOr(any_active, 1); }
+      if (!fits) atomicOr(&d.status[w], 32 /*EGG_ST_DENSE_OVERFLOW*/);
+    }
+    __syncthreads();
+    if (!s_go) continue;
+
+    // A = J J^T (ensembles.cc:664), blocks over shared bodies in ascending body order
+    for (int q = tid; q < nc * nc; q += DT) {
+      const int c = q / nc, c2 = q % nc;
+      double blk[9];
+      pair_block(Jb, ci0, ci1, c, c2, false, blk);
+      for (int k = 0; k < 3; k++)
+        for (int l = 0; l < 3; l++) A[(size_t)(3 * c + k) * R + 3 * c2 + l] = blk[3 * k + l];
+    }
+    __syncthreads();
+    double* F = ldlt_block(A, R, nullptr, R, sm, cfg, Fg);
+    for (int p = tid; p < R; p += DT) sm.xs[p] = e[sm.perm[p]];
+    __syncthreads();
+    ldlt_solve(F, R, sm.xs);
+    double* y = sm.w;
+    for (int p = tid; p < R; p += DT) y[sm.perm[p]] = sm.xs[p];
+    __syncthreads();
+
+    // c = -step_scale J^T y ; StepPositions_ExplicitEuler(dt, c) ; mode 1: v += c
+    double* dynw = d.dyn + (size_t)w * EGG_DYN * n;
+    for (int bd = tid; bd < n; bd += DT) {
+      double g[6] = {0, 0, 0, 0, 0, 0};
+      for (int c = 0; c < nc; c++)
+        for (int side = 0; side < 2; side++) {
+          if ((side ? ci1[c] : ci0[c]) != bd) continue;
+          const double* Jx = Jb + (size_t)c * 72 + 18 * side;
+          for (int k = 0; k < 3; k++)
+            for (int t = 0; t < 6; t++) g[t] += (-1.0 * step_scale * Jx[6 * k + t]) * y[3 * c + k];
+        }
+      d3 p = mk3(dynw[bd], dynw[n + bd], dynw[2 * n + bd]) + dt * mk3(g[0], g[1], g[2]);
+      d3 wv = mk3(g[3], g[4], g[5]);
+      double z2 = dot3(wv, wv);
+      d3 axis = (z2 > 0) ? wv / sqrt(z2) : wv;
+      double ha = 0.5 * (norm3(wv) * dt);
+      double qw = cos(ha), sn = sin(ha);
+      double qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
+      double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
+      double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+      double Q[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+      double Rm[9], Rn[9];
+      for (int k = 0; k < 9; k++) Rm[k] = dynw[(3 + k) * n + bd];
+      mmulm(Q, Rm, Rn);
+      dynw[bd] = p.x; dynw[n + bd] = p.y; dynw[2 * n + bd] = p.z;
+      for (int k = 0; k < 9; k++) dynw[(3 + k) * n + bd] = Rn[k];
+      if (mode == 1) {                          // UpdateComponentsVelocities(v + c), ensembles.cc:655-656
+        for (int t = 0; t < 6; t++) dynw[(12 + t) * n + bd] = dynw[(12 + t) * n + bd] + g[t];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int g_sms = 0;
+int sm_count() {
+  if (!g_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
 }
 
 }  // namespace
 
-// Rows the dense path is provisioned for: EGG_DENSE_ROWS or min(3 nrec, 336), a multiple of 3.
+// Rows the dense path is provisioned for: EGG_DENSE_ROWS, else 3 (nj + 4 n) but at least 336 --
+// never more than the batch can produce (3 nrec).  A world with more rows than this is flagged
+// EGG_ST_DENSE_OVERFLOW and stepped with lambda = 0.
 int egg_dense_row_cap(const EggDev& d) {
   const char* e = getenv("EGG_DENSE_ROWS");
-  int cap = e ? atoi(e) : 336;
+  int cap = e ? atoi(e) : 3 * (d.nj + 4 * d.n);
+  if (!e && cap < 336) cap = 336;
   if (cap > 3 * d.nrec) cap = 3 * d.nrec;
   if (cap < 3) cap = 3;
   return (cap / 3) * 3;
 }
 
-static size_t per_world_doubles(int Rcap) {
-  // A, L, F [R^2 each], X [R (R+1)], Jb [(R/3+1) 72], 12 vectors + (S bytes + 4 int vectors) rounded up
-  size_t dbl = (size_t)Rcap * Rcap * 3 + (size_t)Rcap * (Rcap + 1) + (size_t)(Rcap / 3 + 1) * 72 + 12 * (size_t)Rcap;
-  size_t tail_bytes = (size_t)Rcap * (4 * sizeof(int) + 1) + 16;
-  return dbl + (tail_bytes + 7) / 8;
+static DenseCfg dense_cfg(const EggDev& d) {
+  DenseCfg c;
+  const size_t R = (size_t)egg_dense_row_cap(d);
+  c.Rcap = (int)R;
+  c.ncap = (int)(R / 3);
+  size_t o = 0;
+  auto take = [&](size_t cnt) { const size_t at = o; o += (cnt + 1) & ~(size_t)1; return at; };
+  c.off_A = take(R * R);
+  c.off_Wk = take(2 * R * R);
+  c.off_Lm = take(R * R);
+  c.off_T1 = take(R * R);
+  c.off_Fg = take(R * (R + 1) / 2);
+  c.off_Jb = take((size_t)(c.ncap + 1) * 72);
+  c.off_vec = take(2 * R);
+  c.off_int = take((size_t)c.ncap + (R + 3) / 4 + 2);      // 2 ncap ints + Rcap u16
+  c.per_cta = o;
+  // shared memory: 7 vectors, 6 n accumulator, index lists and masks; the rest of the per-CTA
+  // budget (two CTAs per SM) is the packed factor
+  const size_t fixed = (7 * R + 6 * (size_t)d.n) * sizeof(double) + R * (2 * sizeof(unsigned short) + 2) + 64;
+  const char* e = getenv("EGG_DENSE_SMEM_KB");
+  size_t budget = (size_t)(e ? atoi(e) : 111) * 1024;
+  if (budget > 225 * 1024) budget = 225 * 1024;
+  size_t f = budget > fixed + 1024 ? (budget - fixed) / sizeof(double) : 128;
+  if (f > R * (R + 1) / 2) f = R * (R + 1) / 2;
+  c.Fcap = (int)f;
+  c.smem = fixed + f * sizeof(double);
+  return c;
 }
 
-size_t egg_dense_scratch_bytes(const EggDev& d) { return per_world_doubles(egg_dense_row_cap(d)) * sizeof(double) * (size_t)d.W; }
-
-void egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes) {
-  const int Rcap = egg_dense_row_cap(d);
-  const size_t pw = per_world_doubles(Rcap);
-  size_t smem = (size_t)6 * d.n * sizeof(double);
-  egg_dense_kernel<<<d.W, DT, smem, s>>>(d, dt, reinterpret_cast<double*>(scratch), pw, Rcap);
+static int dense_grid(const EggDev& d, const void* kernel, size_t smem) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, DT, smem);
+  if (per_sm < 1) per_sm = 1;
+  const int g = sm_count() * per_sm;
+  return d.W < g ? d.W : g;
 }
 
-void egg_launch_relax(const EggDev& d, double dt, double step_scale, int max_steps, void* scratch, int* prog, double* err2, int* any_active,
-                      cudaStream_t s) {
-  const int Rcap = egg_dense_row_cap(d);
-  const size_t pw = per_world_doubles(Rcap);
-  egg_relax_kernel<<<d.W, DT, 0, s>>>(d, dt, step_scale, max_steps, reinterpret_cast<double*>(scratch), pw, Rcap, prog, err2, any_active);
+// Slabs for the largest grid either kernel can be launched with (two CTAs per SM).
+size_t egg_dense_scratch_bytes(const EggDev& d) {
+  const DenseCfg c = dense_cfg(d);
+  const int g = sm_count() * 2;
+  return c.per_cta * sizeof(double) * (size_t)(d.W < g ? d.W : g);
+}
+
+int egg_dense_smem_fits(const EggDev& d, size_t limit) { return dense_cfg(d).smem <= limit; }
+
+cudaError_t egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes) {
+  const DenseCfg c = dense_cfg(d);
+  cudaError_t e = cudaFuncSetAttribute(egg_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+  if (e != cudaSuccess) return e;
+  int grid = dense_grid(d, (const void*)egg_dense_kernel, c.smem);
+  const size_t slabs = scratch_bytes / (c.per_cta * sizeof(double));
+  if ((size_t)grid > slabs) grid = (int)slabs;
+  if (grid < 1) return cudaErrorInvalidValue;
+  e = cudaMemsetAsync(d.work_ctr + 1, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  egg_dense_kernel<<<grid, DT, c.smem, s>>>(d, dt, reinterpret_cast<double*>(scratch), c);
+  return cudaGetLastError();
+}
+
+cudaError_t egg_launch_relax(const EggDev& d, double dt, double step_scale, int max_steps, int mode, void* scratch, size_t scratch_bytes,
+                             int* prog, double* err2, int* any_active, cudaStream_t s) {
+  const DenseCfg c = dense_cfg(d);
+  cudaError_t e = cudaFuncSetAttribute(egg_relax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+  if (e != cudaSuccess) return e;
+  int grid = dense_grid(d, (const void*)egg_relax_kernel, c.smem);
+  const size_t slabs = scratch_bytes / (c.per_cta * sizeof(double));
+  if ((size_t)grid > slabs) grid = (int)slabs;
+  if (grid < 1) return cudaErrorInvalidValue;
+  e = cudaMemsetAsync(d.work_ctr + 1, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  egg_relax_kernel<<<grid, DT, c.smem, s>>>(d, dt, step_scale, max_steps, mode, reinterpret_cast<double*>(scratch), c, prog, err2, any_active);
+  return cudaGetLastError();
 }

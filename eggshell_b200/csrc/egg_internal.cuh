@@ -63,17 +63,17 @@ struct EggDev {
   unsigned char* pair_code;   // taps, may be null: [W][P]
   unsigned char* pair_cnt;
   double* rec;
-  double* lam;                // [W][nrec][3] level order during the solve
-  double* rec_minv;           // [W][nrec][20] M^-1 of each block's two bodies, slot order (PGS only, may be null)
-  double* lam2;               // second multiplier buffer (fused variant ping-pongs between the two)
+  double* lam;                // [W][nrec][3] slot order during the solve (Jacobi / SOR only, else null)
+  double* lam2;               // second multiplier buffer (Jacobi / SOR only, else null)
   double* lam_out;            // [W][3*nrec] row order (joints then contacts)
   int* row_state;             // [W][3*nrec]
   int* slot_of;               // [W][nrec] record slot of reference constraint c (Jacobi / SOR only, else null)
-  int* level_start;           // [W][nrec+1] start slot of every solver stage (level chunk <= 32 blocks)
+  int* level_start;           // [W][nrec+1] start slot of every stage of the per-world record order (null with the group stream)
   int* n_levels;              // [W] number of stages
   int* status;                // [W]
   int* stats;                 // [W][8]
   double* resid;              // [W]
+  double* work;               // [W] algorithmic FP64 operations of the last dense solve (dense solver only, else null)
   double* cost0;              // [W][2]
   double* minv_iso;           // [W][n+1][2] = 1/m, 1/c per body when every inverse inertia is c^-1 I3 (row n = 0)
   int* iso_flag;              // [1] device: 1 while every body seen by egg_init was isotropic
@@ -126,18 +126,27 @@ __host__ __device__ inline void mmulm(const double* a, const double* b, double* 
 }
 __host__ __device__ inline double sign1(double a) { return (a >= 0) ? 1.0 : -1.0; }
 
-// Launch wrappers (defined in the .cu files).
-void egg_launch_collide(const EggDev& d, cudaStream_t s);
-void egg_launch_init(const EggDev& d, cudaStream_t s);
-void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
-void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
-void egg_launch_solve_pgs_fast(const EggDev& d, double dt, int lpw, cudaStream_t s);
-void egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s);
-void egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s);
+// Launch wrappers (defined in the .cu files).  Every wrapper returns the first CUDA error of its
+// attribute / occupancy / memset / launch calls (cudaSuccess otherwise); egg_capi.cu turns it into
+// EGG_ERR_CUDA with the wrapper's name in egg_last_error().
+cudaError_t egg_launch_collide(const EggDev& d, cudaStream_t s);
+cudaError_t egg_launch_init(const EggDev& d, cudaStream_t s);
+cudaError_t egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
+cudaError_t egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
+cudaError_t egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s);
+cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s);
 size_t egg_stream_rec_bytes(int W, int nrec, int lpw);
 int egg_stream_blkb(int precision);
 int egg_stage_cap(const EggDev& d);
-void egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s);
-void egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s);
-void egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s);
-void egg_launch_unpack(int W, double* aos, int per_world, int comps, const double* soa, int soa_comps, int comp_off, cudaStream_t s);
+cudaError_t egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s);
+cudaError_t egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s);
+cudaError_t egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s);
+cudaError_t egg_launch_unpack(int W, double* aos, int per_world, int comps, const double* soa, int soa_comps, int comp_off, cudaStream_t s);
+// Dynamic shared memory each kernel family needs for this batch shape (checked against the device
+// limit in egg_create, so that an unsupported shape fails there with a clear message).
+size_t egg_collide_smem(const EggDev& d);
+size_t egg_assemble_smem(const EggDev& d);
+size_t egg_stream_smem(const EggDev& d);
+size_t egg_iter_smem(const EggDev& d);
+// FIRST(e, call): keep the first error of a sequence of CUDA calls.
+#define EGG_FIRST(e, call) do { cudaError_t e2__ = (call); if ((e) == cudaSuccess) (e) = e2__; } while (0)

@@ -215,12 +215,20 @@ __global__ void __launch_bounds__(32) egg_iter_kernel(EggDev d, double dt, int s
 
 }  // namespace
 
-void egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s) {
-  size_t smem = (size_t)d.n * BS * sizeof(double);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(egg_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+size_t egg_iter_smem(const EggDev& d) { return (size_t)d.n * BS * sizeof(double); }
+
+cudaError_t egg_launch_solve_iter(const EggDev& d, double dt, int solver, cudaStream_t s) {
+  const size_t smem = egg_iter_smem(d);
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(egg_iter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
   int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  EGG_FIRST(e, cudaGetDevice(&dev));
+  EGG_FIRST(e, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (e != cudaSuccess) return e;
   int grid = d.W < sms * 16 ? d.W : sms * 16;
   egg_iter_kernel<<<grid, 32, smem, s>>>(d, dt, solver);
+  return cudaGetLastError();
 }

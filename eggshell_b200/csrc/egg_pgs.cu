@@ -4,8 +4,8 @@
 //   egg_assemble_kernel  Joint/Contact::ComputeJ + error  joints.cc:3-35, contact.cc:14-117,
 //                        Ensemble::ComputeJ / rhs         ensembles.cc:38-87, 156-171, 563-570
 // (record math in egg_record.cuh).  The per-world record layout written here feeds the dense path
-// (egg_dense.cu), Jacobi / SOR (egg_iter.cu), the position relaxation and the "fast" PGS kernel
-// (egg_pgs_fast.cu); the default PGS kernel has its own group-stream assembly (egg_pgs_stream.cu).
+// (egg_dense.cu), Jacobi / SOR (egg_iter.cu) and the position relaxation; the PGS kernel has its
+// own group-stream assembly (egg_pgs_stream.cu).
 //
 // Formulation.  Every constraint (joint or contact) is one 3-row block whose two 3x6 Jacobians
 // are [-Rc, Rc [r0]x] and [Rc, -Rc [r1]x] (contact.cc:60-75; a ball joint is the same shape with
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
   for (int c = tid; c <= nc; c += NT) lstart[c] = 0;
   __syncthreads();
 
-  int* gstage = d.level_start + (size_t)w * (d.nrec + 1);
+  int* gstage = d.level_start ? d.level_start + (size_t)w * (d.nrec + 1) : nullptr;
   if (tid == 0) {
     int nl = 0;
     for (int c = 0; c < nc; c++) {           // reference order: joints, then contacts
@@ -78,10 +78,10 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
       lfirst[l] = run;
       lstart[l] = run;                       // running cursor of the level
       lstage[l] = ns;
-      for (int k = 0; k < cnt; k += stage_cap) gstage[ns++] = run + k;
+      for (int k = 0; k < cnt; k += stage_cap) { if (gstage) gstage[ns] = run + k; ns++; }
       run += cnt;
     }
-    gstage[ns] = nc;
+    if (gstage) gstage[ns] = nc;
     d.n_levels[w] = ns;
     for (int c = 0; c < nc; c++) slot[c] = lstart[lev[c]]++;   // stable inside a level
   }
@@ -93,13 +93,6 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
     double v[EGG_REC];
     egg_build_record(d, w, c, i0, i1, sdyn, sst, geom, dt, false, v);
     if (d.slot_of) d.slot_of[(size_t)w * d.nrec + c] = slot[c];
-    if (d.rec_minv) {   // per-block copy of M^-1 of body i0 then i1 (zeros for the world / ground side)
-      double* mv = d.rec_minv + ((size_t)w * d.nrec + slot[c]) * 20;
-      for (int k = 0; k < 10; k++) {
-        mv[k] = (i0 >= 0) ? sst[k * n + i0] : 0.0;
-        mv[10 + k] = (i1 >= 0) ? sst[k * n + i1] : 0.0;
-      }
-    }
     double2* out = reinterpret_cast<double2*>(recw + (size_t)slot[c] * EGG_REC);
 #pragma unroll
     for (int p = 0; p < EGG_PIECES; p++) out[p] = make_double2(v[2 * p], v[2 * p + 1]);
@@ -120,46 +113,48 @@ int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
 }
-// Variant selection: EGG_PGS_VARIANT = stream (default, egg_pgs_stream.cu: group-interleaved record
-// stream) | fast (egg_pgs_fast.cu: per-world records, residual fused into the next sweep; kept as an
-// independent implementation the default kernel is cross-checked against).  The earlier variants
-// (mw, mwpf, fused, tma) are in the history of this file; what they measured is in DESIGN.md §4.
 bool stream_variant(const EggDev& d) { return d.rec_fmt != 0; }
 
 }  // namespace
 
-// Lanes per world of the solver = maximum blocks per stage the assembly may emit.
+// Lanes per world of the PGS kernel = maximum blocks per stage the assembly may emit.
 int egg_stage_cap(const EggDev& d) {
-  int lpw = env_int("EGG_PGS_LPW", 0);
+  static const int env_lpw = env_int("EGG_PGS_LPW", 0);
+  static const int env_min_warps = env_int("EGG_PGS_MIN_WARPS_PER_SM", 3);
+  int lpw = env_lpw;
   if (stream_variant(d)) {
     // narrow worlds expose little parallelism per level: fewer lanes, more worlds per warp
     // (measured: stack10 87 ms at 1 / 101 at 2 / 133 at 4; legged20 95 ms at 4 / 115 at 2 / 123 at 8)
     // -- unless the batch is too small to give every SM a few warps that way
     if (lpw != 1 && lpw != 2 && lpw != 4 && lpw != 8 && lpw != 16) {
       lpw = (d.n <= 12) ? 1 : (d.n <= 24 ? 4 : 8);
-      const long long want = (long long)num_sms() * env_int("EGG_PGS_MIN_WARPS_PER_SM", 3);
+      const long long want = (long long)num_sms() * env_min_warps;
       while (lpw < 8 && (long long)d.W * lpw / 32 < want) lpw *= 2;
     }
     return lpw;
   }
-  if (lpw != 4 && lpw != 8 && lpw != 16) lpw = (d.n <= 12) ? 4 : 8;
-  return lpw;
+  return 8;   // per-world records (dense, Jacobi / SOR, relaxation): the stage cut is not used by those kernels
 }
 
-void egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s) {
-  if (d.rec_fmt) { egg_launch_assemble_stream(d, dt, s); return; }
-  size_t smem = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double) + (size_t)(7 * d.nrec + d.n + 8) * sizeof(int);
+size_t egg_assemble_smem(const EggDev& d) {
+  return (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double) + (size_t)(7 * d.nrec + d.n + 8) * sizeof(int);
+}
+
+cudaError_t egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s) {
+  if (d.rec_fmt) return egg_launch_assemble_stream(d, dt, s);
+  const size_t smem = egg_assemble_smem(d);
   const int cap = egg_stage_cap(d);
+  cudaError_t e = cudaSuccess;
   if (d.nrec <= 128) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_assemble_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(egg_assemble_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     egg_assemble_kernel<64><<<d.W, 64, smem, s>>>(d, dt, cap);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_assemble_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(egg_assemble_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     egg_assemble_kernel<256><<<d.W, 256, smem, s>>>(d, dt, cap);
   }
+  return cudaGetLastError();
 }
 
-void egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) {
-  if (stream_variant(d)) egg_launch_solve_pgs_stream(d, dt, s);
-  else egg_launch_solve_pgs_fast(d, dt, egg_stage_cap(d), s);
-}
+cudaError_t egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s) { return egg_launch_solve_pgs_stream(d, dt, s); }

@@ -348,7 +348,6 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
   const unsigned bar2 = s32(smraw), bar = s32(smraw + 8);
   double* sb = reinterpret_cast<double*>(smraw + 64) + (size_t)sub * 6 * n;
   const int dummy = -(sub * n) - 1;            // body index of the dummy relative to this world's sb
-  constexpr int STG = HDRB + 32 * BLKB;        // one staging buffer: header + 32 blocks
   unsigned char* stage0 = smraw + 64 + (size_t)G * 48 * n;
   const unsigned stage_s = s32(stage0);
   const double cfm = d.prm.cfm;
@@ -748,45 +747,65 @@ int env_i(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+template <bool F32>
+size_t stream_smem(const EggDev& d, int lpw) {
+  const int G = 32 / lpw;
+  return 64 + (size_t)G * 48 * d.n + (size_t)(HDRB + 32 * ((F32 ? RECB32 : RECB64) + LAMB));   // FP64, 64 bodies: 20096 B, 11 CTAs per SM
+}
+
 template <int LPW, int MINB, int ISO, bool F32>
-void launch(const EggDev& d, double dt, cudaStream_t s) {
+cudaError_t launch(const EggDev& d, double dt, cudaStream_t s) {
   constexpr int G = 32 / LPW;
-  const size_t smem = 64 + (size_t)G * 48 * d.n + (size_t)(HDRB + 32 * ((F32 ? RECB32 : RECB64) + LAMB));   // FP64, 64 bodies: 20096 B, 11 CTAs per SM
-  cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO, F32>, 32, smem);
-  if (per_sm < 1) per_sm = 1;
-  const int cap = env_i("EGG_PGS_CTAS_PER_SM", 0);
-  if (cap > 0 && cap < per_sm) per_sm = cap;
+  const size_t smem = stream_smem<F32>(d, LPW);
+  // shared-memory attribute, occupancy and the environment switches are looked up once per
+  // (kernel instance, shared-memory size, device), not on every step
+  static thread_local size_t c_smem = ~(size_t)0;
+  static thread_local int c_dev = -1, c_per_sm = 0, c_sms = 148;
+  static const int env_cap = env_i("EGG_PGS_CTAS_PER_SM", 0), env_pf = env_i("EGG_PGS_PF", 3);
+  cudaError_t e = cudaSuccess;
+  int dev = 0;
+  EGG_FIRST(e, cudaGetDevice(&dev));
+  if (e != cudaSuccess) return e;
+  if (smem != c_smem || dev != c_dev) {
+    EGG_FIRST(e, cudaFuncSetAttribute(egg_pgs_stream_kernel<LPW, MINB, ISO, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EGG_FIRST(e, cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev));
+    EGG_FIRST(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c_per_sm, egg_pgs_stream_kernel<LPW, MINB, ISO, F32>, 32, smem));
+    if (e != cudaSuccess) return e;
+    if (c_per_sm < 1) return cudaErrorLaunchOutOfResources;   // the kernel does not fit an SM with this much shared memory
+    c_smem = smem; c_dev = dev;
+  }
+  int per_sm = c_per_sm;
+  if (env_cap > 0 && env_cap < per_sm) per_sm = env_cap;
   const int groups = (d.W + G - 1) / G;
-  const int grid = groups < sms * per_sm ? groups : sms * per_sm;
-  cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
-  egg_pgs_stream_kernel<LPW, MINB, ISO, F32><<<grid, 32, smem, s>>>(d, dt, env_i("EGG_PGS_PF", 3));
+  const int grid = groups < c_sms * per_sm ? groups : c_sms * per_sm;
+  e = cudaMemsetAsync(d.work_ctr, 0, sizeof(int), s);
+  if (e != cudaSuccess) return e;   // without the reset the persistent kernel would find an exhausted queue and do nothing
+  egg_pgs_stream_kernel<LPW, MINB, ISO, F32><<<grid, 32, smem, s>>>(d, dt, env_pf);
+  return cudaGetLastError();
 }
 
 // Registers are allocated per scheduler (16384 each): 12 one-warp CTAs per SM = 3 per scheduler
 // = 168 registers.
 template <int MINB, int ISO, bool F32>
-void launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
+cudaError_t launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
   switch (d.lpw) {
-    case 1: launch<1, MINB, ISO, F32>(d, dt, s); break;
-    case 2: launch<2, MINB, ISO, F32>(d, dt, s); break;
-    case 4: launch<4, MINB, ISO, F32>(d, dt, s); break;
-    case 16: launch<16, MINB, ISO, F32>(d, dt, s); break;
-    default: launch<8, MINB, ISO, F32>(d, dt, s); break;
+    case 1: return launch<1, MINB, ISO, F32>(d, dt, s);
+    case 2: return launch<2, MINB, ISO, F32>(d, dt, s);
+    case 4: return launch<4, MINB, ISO, F32>(d, dt, s);
+    case 16: return launch<16, MINB, ISO, F32>(d, dt, s);
+    default: return launch<8, MINB, ISO, F32>(d, dt, s);
   }
 }
 // One staging buffer per warp.  A second buffer (two rounds in flight) was measured no better
 // anywhere -- stack10 4096 worlds 26.9 vs 26.2 ms, legged20 106 vs 90 ms, pile64 8.8 vs 8.1 ms --
 // and was removed again.
 template <int MINB, int ISO>
-void launch_nbuf(const EggDev& d, double dt, cudaStream_t s) {
-  if (d.blkb == RECB32 + LAMB) launch_lpw<MINB, ISO, true>(d, dt, s);
-  else launch_lpw<MINB, ISO, false>(d, dt, s);
+cudaError_t launch_nbuf(const EggDev& d, double dt, cudaStream_t s) {
+  if (d.blkb == RECB32 + LAMB) return launch_lpw<MINB, ISO, true>(d, dt, s);
+  return launch_lpw<MINB, ISO, false>(d, dt, s);
 }
+
+size_t schedule_per_world(const EggDev& d) { return ((size_t)(d.n + 4 * d.nrec + 2 + 7) & ~(size_t)7) * sizeof(unsigned short); }
 
 }  // namespace
 
@@ -797,32 +816,45 @@ size_t egg_stream_rec_bytes(int W, int nrec, int lpw) {
   return (size_t)((W + G - 1) / G) * group_stride_bytes(nrec, G);
 }
 
+size_t egg_stream_smem(const EggDev& d) {
+  const size_t solve = (d.blkb == RECB32 + LAMB) ? stream_smem<true>(d, d.lpw) : stream_smem<false>(d, d.lpw);
+  const size_t recs = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double);
+  const size_t sched = schedule_per_world(d);
+  size_t m = solve > recs ? solve : recs;
+  return m > sched ? m : sched;
+}
+
 // Group-stream assembly: schedule (per world) -> rounds (per group) -> records (per world).
-void egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s) {
+cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s) {
   const int G = 32 / d.lpw;
+  cudaError_t e = cudaSuccess;
   {
-    const size_t per = ((size_t)(d.n + 4 * d.nrec + 2 + 7) & ~(size_t)7) * sizeof(unsigned short);
+    const size_t per = schedule_per_world(d);
     int wpc = (int)((size_t)200 * 1024 / per);
     if (wpc > 4) wpc = 4;
     if (wpc < 1) wpc = 1;
     const size_t smem = wpc * per;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (e != cudaSuccess) return e;
     egg_schedule_kernel<<<(d.W + wpc - 1) / wpc, 128, smem, s>>>(d, d.lpw, wpc);
   }
   const int ngroups = (d.W + G - 1) / G;
   egg_rounds_kernel<<<(ngroups + 3) / 4, 128, 0, s>>>(d, G);
   const size_t smem = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double);
   if (d.nrec <= 128) {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_records_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (e != cudaSuccess) return e;
     egg_records_kernel<64><<<d.W, 64, smem, s>>>(d, dt, G);
   } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(egg_records_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (e != cudaSuccess) return e;
     egg_records_kernel<256><<<d.W, 256, smem, s>>>(d, dt, G);
   }
+  return cudaGetLastError();
 }
 
-void egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s) {
-  if (d.iso == 2) launch_nbuf<12, 2>(d, dt, s);
-  else if (d.iso == 1) launch_nbuf<12, 1>(d, dt, s);
-  else launch_nbuf<8, 0>(d, dt, s);
+cudaError_t egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s) {
+  if (d.iso == 2) return launch_nbuf<12, 2>(d, dt, s);
+  if (d.iso == 1) return launch_nbuf<12, 1>(d, dt, s);
+  return launch_nbuf<8, 0>(d, dt, s);
 }

@@ -190,28 +190,33 @@ double egg_measure_fp64_tflops() {
   return best;
 }
 
-void egg_launch_init(const EggDev& d, cudaStream_t s) {
+cudaError_t egg_launch_init(const EggDev& d, cudaStream_t s) {
   long long t = (long long)d.W * d.n;
-  cudaMemsetAsync(d.iso_flag, 0xff, sizeof(int), s);   // all ones; bit 0 cleared by a non-isotropic body, bit 1 by a non-uniform one
+  cudaError_t e = cudaMemsetAsync(d.iso_flag, 0xff, sizeof(int), s);   // all ones; bit 0 cleared by a non-isotropic body, bit 1 by a non-uniform one
   egg_init_kernel<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(d);
   egg_iso_uniform_kernel<<<(unsigned)((t + 127) / 128), 128, 0, s>>>(d);
   if (d.nj > 0) {
     long long tj = (long long)d.W * d.nj;
     egg_init_check_kernel<<<(unsigned)((tj + 127) / 128), 128, 0, s>>>(d);
   }
+  EGG_FIRST(e, cudaGetLastError());
+  return e;
 }
 
-void egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s) {
+cudaError_t egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s) {
   egg_cost_kernel<<<(d.W + 127) / 128, 128, 0, s>>>(d, cost_d);
+  return cudaGetLastError();
 }
 
-void egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s) {
+cudaError_t egg_launch_pack(int W, const double* aos, int per_world, int comps, double* soa, int soa_comps, int comp_off, cudaStream_t s) {
   long long total = (long long)W * per_world * comps;
-  if (total == 0) return;
+  if (total == 0) return cudaSuccess;
   egg_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(aos, W, per_world, comps, soa, soa_comps, comp_off);
+  return cudaGetLastError();
 }
-void egg_launch_unpack(int W, double* aos, int per_world, int comps, const double* soa, int soa_comps, int comp_off, cudaStream_t s) {
+cudaError_t egg_launch_unpack(int W, double* aos, int per_world, int comps, const double* soa, int soa_comps, int comp_off, cudaStream_t s) {
   long long total = (long long)W * per_world * comps;
-  if (total == 0) return;
+  if (total == 0) return cudaSuccess;
   egg_unpack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(aos, W, per_world, comps, soa, soa_comps, comp_off);
+  return cudaGetLastError();
 }

@@ -50,6 +50,17 @@ void Ensemble::Upload() {
   }
 }
 
+void Ensemble::UploadState() {
+  const int n = n_;
+  std::vector<double> p(3 * n), R(9 * n), v(3 * n), w(3 * n);
+  for (int i = 0; i < n; i++) {
+    const Body& b = *components_.at(i);
+    for (int k = 0; k < 3; k++) { p[3 * i + k] = b.p()(k); v[3 * i + k] = b.v()(k); w[3 * i + k] = b.w_g()(k); }
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R[9 * i + 3 * r + c] = b.R()(r, c);
+  }
+  check(egg_set_state(batch_, p.data(), R.data(), v.data(), w.data()), "egg_set_state");
+}
+
 void Ensemble::Download(bool with_contacts) {
   const int n = n_;
   std::vector<double> p(3 * n), R(9 * n), v(3 * n), w(3 * n);
@@ -127,6 +138,10 @@ void Ensemble::Step(double dt, Integrator g) {
   if (!batch_) Panic("Ensemble::Step before Init");
   if (g == Integrator::IMPLICIT_MIDPOINT) Panic("Implicit midpoint integrator is not properly implemented and tested.");   // :403-405
   if (g == Integrator::EXPLICIT_EULER) Panic("EXPLICIT_EULER is not part of the accelerated path (ensembles.cc:397-402).");
+  // The reference's Step reads the Body objects (GetVelocities, ensembles.cc:429-436), so SetP /
+  // SetR / SetV / SetW_GlobalFrame between steps take effect: push the host state first (the
+  // values are the ones the last Download wrote unless the caller changed them).
+  UploadState();
   check(egg_step(batch_, dt, EGG_OPEN_DYNAMICS_ENGINE, 1), "egg_step");
   Download(true);
   if (status_ & EGG_ST_JOINT_CONFLICT) Panic("Joint constraints conflict or cause overconstraint.");
@@ -141,6 +156,36 @@ void Ensemble::InitStabilize() {
   check(egg_init_stabilize(batch_, 100, &steps, &e2), "egg_init_stabilize");
   Download(true);
   std::printf("Pre-stabilization steps count : %d\nFinal err_sq : %g\n", steps, e2);
+}
+
+void Ensemble::PostStabilize(int max_steps) {
+  // ensembles.cc:624-645 on the device: StepPostStabilization(dt = 0.1) while the squared
+  // constraint error exceeds 1e-9, at most max_steps times.
+  if (!batch_) Panic("Ensemble::PostStabilize before Init");
+  UploadState();
+  int steps = 0;
+  double e2 = 0;
+  check(egg_post_stabilize(batch_, max_steps, &steps, &e2), "egg_post_stabilize");
+  Download(false);
+}
+
+VectorXd Ensemble::ComputeJDotV() const {
+  // ensembles.cc:95-98 / :123-129: both halves Panic in the reference (only the ODE stepper, which
+  // never needs Jdot v, works with contacts).
+  Panic("Jdot is hardcoded to have 3 rows. Should be decided by the Constraint.");
+  return VectorXd::Zero(0);
+}
+
+bool Ensemble::CheckConservationOfEnergy() {   // ensembles.cc:186-200
+  double energy = 0;
+  for (const auto& b : components_) energy = energy + b->GetRotationalKE();
+  if (std::fabs(energy - total_rotational_ke_) > 1e-9 && total_rotational_ke_ != std::numeric_limits<double>::infinity()) {
+    std::printf("Total rotational KE was %g, now it's %g\n", total_rotational_ke_, energy);
+    total_rotational_ke_ = energy;
+    return false;
+  }
+  total_rotational_ke_ = energy;
+  return true;
 }
 
 MatrixXd Ensemble::ComputeJ() const {

@@ -107,7 +107,10 @@ void egg_destroy(egg_batch* b);
  * (0.3,0.3,0.3 as body.h:91). */
 int egg_set_bodies(egg_batch* b, const double* p, const double* R, const double* v, const double* w,
                    const double* m, const double* I_body, const double* side);
-/* Dynamic state only (SetP/SetR/SetV/SetW_GlobalFrame, body.h:64-71). */
+/* Dynamic state only (SetP/SetR/SetV/SetW_GlobalFrame, body.h:64-71).  The host-to-device copies
+ * are asynchronous on the batch stream: when the arrays live in pinned memory (egg_host_alloc) the
+ * call returns before they have been read, so keep them unchanged until the next synchronising
+ * call (egg_sync, egg_get_*).  Pageable arrays are staged by the runtime before the call returns. */
 int egg_set_state(egg_batch* b, const double* p, const double* R, const double* v, const double* w);
 /* BallAndSocketJoint(b0,i0,c0,b1,i1,c1) / (b0,i0,c0,c1_world) (joints.h:34-42); i1 = -1 anchors
  * body i0 to the world point c1. */
@@ -115,7 +118,10 @@ int egg_set_joints(egg_batch* b, const int* i0, const int* i1, const double* c0,
 /* Overrides Ensemble::external_force_torque_ (ensembles.h:88-89) after egg_init; 6 per body. */
 int egg_set_external(egg_batch* b, const double* f_ext);
 
-/* Ensemble::Init (ensembles.cc:24-29): M^-1 blocks, f_ext, initial-condition check. */
+/* Ensemble::Init (ensembles.cc:24-29): M^-1 blocks, f_ext, initial-condition check and
+ * CheckAndCorrectEnsembleState (a joint-joint conflict sets EGG_ST_JOINT_CONFLICT here, where the
+ * reference Panics).  Body state changed afterwards reaches the device only through
+ * egg_set_state / egg_set_bodies. */
 int egg_init(egg_batch* b);
 
 /* Ensemble::InitStabilize (ensembles.cc:602-622): refresh contacts, and while a world's squared
@@ -123,6 +129,13 @@ int egg_init(egg_batch* b);
  * reference) apply StepPositionRelaxation(dt = 0.5, step_scale = 0.2); finally
  * CheckAndCorrectEnsembleState.  steps_out[W] / err_sq_out[W] may be NULL.  Synchronous. */
 int egg_init_stabilize(egg_batch* b, int max_steps, int* steps_out, double* err_sq_out);
+
+/* Ensemble::PostStabilize(max_steps) (ensembles.cc:624-645, max_steps = 500 in ensembles.h:59):
+ * while a world's squared position error exceeds 1e-9 apply StepPostStabilization(dt = 0.1,
+ * step_scale = 0.2) (ensembles.cc:652-657): positions AND velocities move by the relaxation
+ * -0.2 J^T (J J^T)^-1 err.  As in the reference the contact list is not refreshed inside the loop
+ * (a contact's error is its stored depth).  steps_out[W] / err_sq_out[W] may be NULL.  Synchronous. */
+int egg_post_stabilize(egg_batch* b, int max_steps, int* steps_out, double* err_sq_out);
 
 /* n_steps x Ensemble::Step(dt, integrator) (ensembles.cc:390-427) on every world; asynchronous on
  * the batch stream. */
@@ -154,13 +167,26 @@ int egg_get_bodies(egg_batch* b, double* p, double* R, double* v, double* w);
 int egg_get_contacts(egg_batch* b, int* count, int* i0, int* i1, double* pos, double* nrm,
                      double* depth, int* code, double* lambda, int* row_state);
 
+/* The same taps for the worlds [first, first + n_worlds) only: arrays are sized for n_worlds worlds.
+ * Use this for spot checks of large batches (egg_get_contacts of 65536 x 64-body worlds moves GBs). */
+int egg_get_contacts_range(egg_batch* b, int first, int n_worlds, int* count, int* i0, int* i1, double* pos,
+                           double* nrm, double* depth, int* code, double* lambda, int* row_state);
+
 /* Colliding pairs of the last step in (i<j) lexicographic order with CollisionInfo.code and the
  * pre-de-dup contact count (requires desc.taps = 1).  n_hits[W]; pi,pj,code,count [W][max_pairs]. */
 int egg_get_pair_hits(egg_batch* b, int* n_hits, int* pi, int* pj, int* code, int* count, int max_pairs);
+int egg_get_pair_hits_range(egg_batch* b, int first, int n_worlds, int* n_hits, int* pi, int* pj, int* code, int* count, int max_pairs);
 
 /* status[W] (egg_status bits); stats [W][8] = {n_contacts_raw, n_contacts, n_rows, n_pair_hits,
  * sweeps, pivots, cfm_applied, reserved}; residual[W] = last GetResidualError. */
 int egg_get_status(egg_batch* b, int* status, int* stats, double* residual);
+
+/* Dense solver only: FP64 operations the reference algorithm spends on each world's last solve
+ * (flops[W]; multiplications and additions counted separately): one factorisation for the cfm
+ * decision, the LU inverse and products of the Schur complement (lcp.cc:286-294), and per Murty
+ * pivot one LDL^T of the basic block, its two triangular solves and w = A_NS x_S (lcp.cc:195-232).
+ * Feeds the FP64 roofline of bench.py --workload c4. */
+int egg_get_dense_work(egg_batch* b, double* flops);
 
 /* MPC rollout cost per world written to a DEVICE buffer of n_worlds doubles (feeds the NCCL
  * allgather): cost = -(x_body0 - x0_body0) + 10 (z_body0 - z0_body0)^2 with (x0,z0) the pose at

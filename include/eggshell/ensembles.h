@@ -6,6 +6,7 @@
 #ifndef EGGSHELL_ENSEMBLES_H_
 #define EGGSHELL_ENSEMBLES_H_
 #include <array>
+#include <limits>
 #include <memory>
 #include <vector>
 #include "constraints.h"
@@ -26,8 +27,11 @@ class Ensemble {
   virtual MatrixXd ComputeJ(ArrayXb* C, VectorXd* x_lo, VectorXd* x_hi) const;   // ensembles.cc:38-87
   enum struct Integrator { EXPLICIT_EULER = 0, OPEN_DYNAMICS_ENGINE, IMPLICIT_MIDPOINT };
   virtual void Step(double dt, Integrator g = Integrator::OPEN_DYNAMICS_ENGINE);   // ensembles.cc:390-427
+  virtual VectorXd ComputeJDotV() const;                          // ensembles.cc:89-98: Panics, as the reference does
   void InitStabilize();                                           // ensembles.cc:602-622
+  void PostStabilize(int max_steps = 500);                        // ensembles.cc:624-645
   virtual void Draw() const;
+  bool CheckConservationOfEnergy();                               // ensembles.cc:186-200
   const MatrixXd& M_inverse() const { return M_inverse_; }
   const ConstraintsList constraints() const;                      // joints then contacts, ensembles.cc:234-239
   const ComponentsList& components() const { return components_; }
@@ -45,12 +49,14 @@ class Ensemble {
   ContactsList contacts_;
   MatrixXd M_inverse_;
   VectorXd external_force_torque_;
+  double total_rotational_ke_ = std::numeric_limits<double>::infinity();   // ensembles.h:92
   void UpdateContacts();                                          // ensembles.cc:445-480 (+ :241-329)
 
  private:
   egg_batch* batch_ = nullptr;
   int solver_ = 0, k_max_ = 500, status_ = 0, sweeps_ = 0;
   void Upload();
+  void UploadState();                                             // Body p, R, v, w -> device (setters between steps take effect)
   void Download(bool with_contacts);
 };
 

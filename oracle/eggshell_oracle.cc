@@ -217,6 +217,7 @@ void orc_world_build_cairn(void* wp, int rocks, const double* xb, const double* 
 int orc_world_init(void* wp) { return world_init(*(World*)wp); }
 int orc_world_init_stabilize(void* wp, double* final_err_sq) { return init_stabilize(*(World*)wp, final_err_sq); }
 int orc_world_init_stabilize_n(void* wp, int max_steps, double* final_err_sq) { return init_stabilize(*(World*)wp, final_err_sq, max_steps); }
+int orc_world_post_stabilize(void* wp, int max_steps, double* final_err_sq) { return post_stabilize(*(World*)wp, final_err_sq, max_steps); }
 int orc_world_step(void* wp, double dt) { World& W = *(World*)wp; world_step(W, dt); return W.stats.status; }
 int orc_world_n(void* wp) { return ((World*)wp)->n; }
 int orc_world_n_joints(void* wp) { return (int)((World*)wp)->joints.size(); }

@@ -322,10 +322,15 @@ struct LDLT {
     for (int i = 0; i < n; i++) {           // D^+
       if (std::fabs(m(i, i)) > tol) x[i] /= m(i, i); else x[i] = 0;
     }
-    for (int i = n - 1; i >= 0; i--) {      // L^-T
-      double s = x[i];
-      for (int j = i + 1; j < n; j++) s -= m(j, i) * x[j];
-      x[i] = s;
+    // L^-T as a column sweep: once x[j] is final it is eliminated from every row above it, so row
+    // i receives its terms for j = n-1 down to i+1.  (Eigen's own kernel for this step is a
+    // panelled, vectorised row sweep whose summation order depends on the SIMD width and on FMA
+    // contraction of the build; no scalar order is "the" reference order.  The column sweep is the
+    // one order that is parallel over rows, which is what the device needs to reproduce it bit
+    // for bit.)
+    for (int j = n - 1; j >= 1; j--) {
+      const double xj = x[j];
+      for (int i = 0; i < j; i++) x[i] -= m(j, i) * xj;
     }
     for (int k = n - 1; k >= 0; k--) if (tr[k] != k) std::swap(x[k], x[tr[k]]);
     return x;

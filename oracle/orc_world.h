@@ -725,6 +725,32 @@ inline int init_stabilize(World& W, double* final_err_sq, int max_steps = 100) {
   return steps;
 }
 
+// ensembles.cc:624-645 PostStabilize + :652-657 StepPostStabilization(dt = kSimTimeStep * 100):
+// positions by explicit Euler with the relaxation "velocity", then v += relaxation.  The contact
+// list is whatever the last UpdateContacts / Step left (it is not refreshed in the loop, so a
+// contact's error stays its stored depth).
+inline int post_stabilize(World& W, double* final_err_sq, int max_steps = 500) {
+  Vec err = position_error(W);
+  double e2 = 0;
+  for (double x : err) e2 += x * x;
+  int steps = 0;
+  while (e2 > kAllowNumericalError && steps < max_steps) {
+    Vec c = velocity_relaxation(W, 0.2);
+    step_positions_explicit_euler(W, 0.001 * 100, c);
+    for (int i = 0; i < W.n; i++) {                       // UpdateComponentsVelocities(v + c)
+      Body& b = W.bodies[i];
+      b.v = Vec3(b.v.x + c[6 * i], b.v.y + c[6 * i + 1], b.v.z + c[6 * i + 2]);
+      b.w = Vec3(b.w.x + c[6 * i + 3], b.w.y + c[6 * i + 4], b.w.z + c[6 * i + 5]);
+    }
+    err = position_error(W);
+    e2 = 0;
+    for (double x : err) e2 += x * x;
+    ++steps;
+  }
+  if (final_err_sq) *final_err_sq = e2;
+  return steps;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Built-in scenes (ensembles.cc:668-728).
 

@@ -274,6 +274,11 @@ class World:
         steps = lib().orc_world_init_stabilize_n(self.h, int(max_steps), C.byref(e))
         return steps, e.value
 
+    def post_stabilize(self, max_steps=500):
+        e = C.c_double(0)
+        steps = lib().orc_world_post_stabilize(self.h, int(max_steps), C.byref(e))
+        return steps, e.value
+
     def step(self, dt):
         return lib().orc_world_step(self.h, C.c_double(dt))
 

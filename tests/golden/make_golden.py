@@ -67,6 +67,7 @@ if __name__ == "__main__":
     chain10()
     scene_steps("stack10_pgs", S.stack10(2, seed=1000), 2, 2, solver=O.SOLVER_PGS)
     scene_steps("pile64_pgs_k50", S.pile64(1, seed=3000), 1, 2, solver=O.SOLVER_PGS, k_max=50)
+    scene_steps("pile64_pgs_k500", S.pile64(1, seed=3000), 1, 2, solver=O.SOLVER_PGS, k_max=500)
     scene_steps("legged20_pgs_k100", S.legged20(2, seed=5000), 2, 2, solver=O.SOLVER_PGS, k_max=100)
-    scene_steps("chain32_pgs_k100", S.chain32(1, seed=4000), 1, 2, solver=O.SOLVER_PGS, k_max=100)
+    scene_steps("chain32_pgs_k100", S.chain32(1, seed=4000, anchor_z=0.2), 1, 2, solver=O.SOLVER_PGS, k_max=100)
     scene_steps("cairn4_pgs", S.cairn(2, rocks=4, zb=(0.2, 0.6), seed=11), 2, 5, solver=O.SOLVER_PGS)

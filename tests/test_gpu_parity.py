@@ -3,12 +3,12 @@ time from shared state.  Discrete outputs bit-exact; p, R, v, w, lambda within 1
 import numpy as np
 import pytest
 
-from tests.helpers import oracle_world, compare_step, rel_err
+from tests.helpers import oracle_world, compare_step, rel_err, SCALE
 
 pytestmark = pytest.mark.gpu
 
 
-def _stepwise(scene, nsteps, worlds_idx, batch_kw, oracle_kw, tol=1e-9, lam_tol=1e-7):
+def _stepwise(scene, nsteps, worlds_idx, batch_kw, oracle_kw, tol=1e-9, lam_tol=1e-9):
     import eggshell_b200 as E
     b = E.scenes.make_batch(scene, taps=True, **batch_kw)
     ows = [oracle_world(scene, wi, **oracle_kw)[0] for wi in worlds_idx]
@@ -22,7 +22,7 @@ def _stepwise(scene, nsteps, worlds_idx, batch_kw, oracle_kw, tol=1e-9, lam_tol=
         b.step(dt)
         for ow in ows:
             ow.step(dt)
-        worst = compare_step(b, ows, worlds_idx, tol=tol)
+        worst = compare_step(b, ows, worlds_idx, tol=tol, lam_tol=lam_tol)
         st = b.status()
         for k, wi in enumerate(worlds_idx):
             os_ = ows[k].stats()
@@ -49,6 +49,25 @@ def test_pile64_pgs_stepwise():
     scene = E.scenes.pile64(4, seed=3000)
     worst = _stepwise(scene, 2, list(range(4)), dict(solver=E.SOLVER_PGS, k_max=50), dict(solver=1, k_max=50))
     print("pile64 worst", worst)
+
+
+def test_pile64_pgs_k500_stepwise():
+    """The benchmarked configuration itself (C3 at the reference's termination, K <= 500 sweeps):
+    4 worlds, 2 steps from shared state; sweep counts and clamp states bit-exact, state and
+    multipliers within 1e-9 (every world runs all 500 sweeps on the interpenetrating lattice)."""
+    import eggshell_b200 as E
+    scene = E.scenes.pile64(4, seed=3000)
+    worst = _stepwise(scene, 2, list(range(4)), dict(solver=E.SOLVER_PGS, k_max=500), dict(solver=1, k_max=500))
+    print("pile64 K=500 worst", worst)
+
+
+@pytest.mark.parametrize("name,W,steps", [("pile64", 4, 2), ("stack10", 8, 3), ("legged20", 4, 3)])
+def test_pgs_fixed_k20_stepwise(name, W, steps):
+    """Fixed-K mode (bench.py's `fixed_k` line, K = 20 sweeps): parity at the same K."""
+    import eggshell_b200 as E
+    scene = getattr(E.scenes, name)(W)
+    worst = _stepwise(scene, steps, list(range(W)), dict(solver=E.SOLVER_PGS, k_max=20), dict(solver=1, k_max=20))
+    print(name, "K=20 worst", worst)
 
 
 def test_cairn_pgs_falling():
@@ -104,33 +123,6 @@ def test_pgs_converging_worlds_take_the_exact_residual_path():
     print("converging worst", worst, "sweeps of step 0", sw.tolist())
 
 
-@pytest.mark.parametrize("name,W,k_max", [("pile64", 6, 40), ("stack10", 37, 200), ("legged20", 11, 100)])
-def test_pgs_stream_matches_legacy_variant(name, W, k_max, monkeypatch):
-    """The default 'stream' kernel (group-interleaved records, probe-based stopping test) against
-    the earlier 'fast' kernel (per-world records, residual every sweep) on the same scenes, with
-    world counts that do not fill the last warp group: same sweep counts and clamp states,
-    multipliers and state within 1e-9."""
-    import eggshell_b200 as E
-    scene = getattr(E.scenes, name)(W)
-    res = {}
-    for variant in ("stream", "fast"):
-        monkeypatch.setenv("EGG_PGS_VARIANT", variant)
-        b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, taps=True)
-        out = []
-        for s in range(2):
-            b.step(scene["dt"])
-            st, con = b.status(), b.contacts()
-            out.append((st["sweeps"].copy(), con["row_state"].copy(), con["lam"].copy(), [x.copy() for x in b.bodies()], st["residual"].copy()))
-        b.close()
-        res[variant] = out
-    for a, c in zip(res["stream"], res["fast"]):
-        assert np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1])
-        assert rel_err(a[2], c[2]) < 1e-9
-        for x, y in zip(a[3], c[3]):
-            assert rel_err(x, y) < 1e-9
-        assert rel_err(a[4], c[4], floor=1e-3) < 1e-6
-
-
 # ---------------------------------------------------------------------------------------------
 # Against the committed golden fixtures (tests/golden/*.npz).
 def _vs_golden(name, scene, nw, ns, batch_kw, tol=1e-9):
@@ -162,8 +154,9 @@ def _vs_golden(name, scene, nw, ns, batch_kw, tol=1e-9):
             assert np.array_equal(con["row_state"][wi, :nr], g[pre + "row_state"])
             for key, val in (("p", p[wi]), ("R", R[wi]), ("v", v[wi]), ("w", w[wi]), ("c_pos", con["pos"][wi, :nc]),
                              ("c_nrm", con["nrm"][wi, :nc]), ("c_depth", con["depth"][wi, :nc])):
-                assert rel_err(val, g[pre + key]) <= tol, (name, wi, s, key, rel_err(val, g[pre + key]))
-            assert rel_err(con["lam"][wi, :nr], g[pre + "lam"]) <= 1e-7
+                sc = SCALE[key[2:] if key.startswith("c_") else key]
+                assert rel_err(val, g[pre + key], sc) <= tol, (name, wi, s, key, rel_err(val, g[pre + key], sc))
+            assert rel_err(con["lam"][wi, :nr], g[pre + "lam"], SCALE["lam"]) <= 1e-9
     b.close()
 
 
@@ -172,8 +165,9 @@ def test_golden_fixtures_pgs():
     S = E.scenes
     _vs_golden("stack10_pgs", S.stack10(2, seed=1000), 2, 2, dict(solver=E.SOLVER_PGS))
     _vs_golden("pile64_pgs_k50", S.pile64(1, seed=3000), 1, 2, dict(solver=E.SOLVER_PGS, k_max=50))
+    _vs_golden("pile64_pgs_k500", S.pile64(1, seed=3000), 1, 2, dict(solver=E.SOLVER_PGS, k_max=500))
     _vs_golden("legged20_pgs_k100", S.legged20(2, seed=5000), 2, 2, dict(solver=E.SOLVER_PGS, k_max=100))
-    _vs_golden("chain32_pgs_k100", S.chain32(1, seed=4000), 1, 2, dict(solver=E.SOLVER_PGS, k_max=100))
+    _vs_golden("chain32_pgs_k100", S.chain32(1, seed=4000, anchor_z=0.2), 1, 2, dict(solver=E.SOLVER_PGS, k_max=100))
     _vs_golden("cairn4_pgs", S.cairn(2, rocks=4, zb=(0.2, 0.6), seed=11), 2, 5, dict(solver=E.SOLVER_PGS))
 
 
@@ -324,7 +318,7 @@ def test_full_size_step_is_bit_reproducible(name, W, k_max, lpw, monkeypatch):
 
 # ---------------------------------------------------------------------------------------------
 # Dense path (what the reference ships): Schur complement + Murty principal pivoting.
-def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-6, oracle_kw=None, **kw):
+def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-9, oracle_kw=None, **kw):
     import eggshell_b200 as E
     b = E.scenes.make_batch(scene, solver=E.SOLVER_DENSE_MURTY, taps=True, **kw)
     ows = [oracle_world(scene, wi, solver=0, **(oracle_kw or {}))[0] for wi in worlds_idx]
@@ -337,7 +331,7 @@ def _stepwise_dense(scene, nsteps, worlds_idx, tol=1e-9, lam_tol=1e-6, oracle_kw
         b.step(dt)
         for ow in ows:
             ow.step(dt)
-        worst = compare_step(b, ows, worlds_idx, tol=tol)
+        worst = compare_step(b, ows, worlds_idx, tol=tol, lam_tol=lam_tol)
         st = b.status()
         con = b.contacts()
         for k, wi in enumerate(worlds_idx):
@@ -366,7 +360,7 @@ def test_dense_chain10_golden():
         b.step(0.001)
         p, R, v, w = b.bodies()
         for key, val in (("p", p[0]), ("R", R[0]), ("v", v[0]), ("w", w[0])):
-            assert rel_err(val, g[f"s{s}_{key}"]) <= 1e-9, (s, key)
+            assert rel_err(val, g[f"s{s}_{key}"], SCALE[key]) <= 1e-9, (s, key)
         st = b.status()
         assert [st["n_contacts_raw"][0], st["n_contacts"][0], st["n_rows"][0], st["n_pair_hits"][0]] == g[f"s{s}_stats"][:4].tolist()
     # contact phase: replay golden states 399 -> 400 -> 401
@@ -382,8 +376,8 @@ def test_dense_chain10_golden():
         nr = len(g[f"s{s}_lam"])
         assert np.array_equal(con["row_state"][0, :nr], g[f"s{s}_row_state"])
         for key, val in (("p", p[0]), ("R", R[0]), ("v", v[0]), ("w", w[0])):
-            assert rel_err(val, g[f"s{s}_{key}"]) <= 1e-9, (s, key)
-        assert rel_err(con["lam"][0, :nr], g[f"s{s}_lam"]) <= 1e-6
+            assert rel_err(val, g[f"s{s}_{key}"], SCALE[key]) <= 1e-9, (s, key)
+        assert rel_err(con["lam"][0, :nr], g[f"s{s}_lam"], SCALE["lam"]) <= 1e-9
     b.close()
 
 
@@ -392,6 +386,169 @@ def test_dense_cairn_and_chain_stepwise():
     npiv = _stepwise_dense(E.scenes.cairn(8, rocks=4, zb=(0.2, 0.5), seed=21), 25, list(range(8)))
     assert npiv > 0
     _stepwise_dense(E.scenes.chain(2, links=6, anchor=(0.0, 0.0, 0.25), seed=5, anchor_jitter=0.05), 6, [0, 1])
+
+
+def test_dense_chain32_stepwise():
+    """C4 (BASELINE.json configs[3]): 32-link chain landing on the ground, dense Schur + Murty
+    (lcp.cc:157-336) with 96 equality rows and 90-150 contact rows.  4 worlds x 6 steps from shared
+    state: pivot counts (70-300 per step), active set and cfm decision bit-exact, state and
+    multipliers within 1e-9."""
+    import eggshell_b200 as E
+    scene = E.scenes.chain32(4, seed=4000)
+    npiv = _stepwise_dense(scene, 6, [0, 1, 2, 3])
+    print("chain32 dense: pivots compared", npiv)
+    assert npiv > 1000
+
+
+def test_dense_chain32_box_bounds():
+    """The same scene with the BOX friction bounds honoured (quirk q1 off)."""
+    import eggshell_b200 as E
+    q = E.QUIRK_GS_BOUNDS_SHIFT
+    scene = E.scenes.chain32(2, seed=4001)
+    npiv = _stepwise_dense(scene, 4, [0, 1], quirks=q, oracle_kw=dict(quirks=q))
+    assert npiv > 0
+
+
+def test_full_size_c4_runs_clean():
+    """16384 worlds x chain32, dense solver, three steps from the scene's start (free fall, landing,
+    resting contact): no world may fail its LCP, overflow the dense row capacity or go non-finite;
+    sampled worlds re-run alone give the same bits and match the oracle."""
+    import eggshell_b200 as E
+    W = 16384
+    scene = E.scenes.chain32(W, seed=4000)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_DENSE_MURTY)
+    for s in range(3):
+        b.step(scene["dt"])
+        st = b.status()
+        assert int(np.bitwise_or.reduce(st["status"])) == 0, (s, np.nonzero(st["status"])[0][:16].tolist(), np.unique(st["status"]).tolist())
+    assert st["n_contacts"].mean() > 20 and st["pivots"].max() < 1000 and st["pivots"].mean() > 30
+    assert int(st["cfm_applied"].min()) == 1
+    big = b.bodies()
+    idx = [0, 7777, W - 1]
+    sub = {k: (val[idx] if isinstance(val, np.ndarray) and val.shape[:1] == (W,) else val) for k, val in scene.items()}
+    sub["W"] = len(idx)
+    b2 = E.scenes.make_batch(sub, solver=E.SOLVER_DENSE_MURTY, taps=True)
+    ows = [oracle_world(scene, wi, solver=0)[0] for wi in idx]
+    for s in range(3):
+        p, R, v, w = b2.bodies()
+        for k in range(len(idx)):
+            ows[k].set_state(p[k], R[k], v[k], w[k])
+        b2.step(scene["dt"])
+        for ow in ows:
+            ow.step(scene["dt"])
+        compare_step(b2, ows, list(range(len(idx))))
+    for a, c in zip(big, b2.bodies()):
+        assert np.array_equal(a[idx], c)
+    b.close(); b2.close()
+
+
+def test_cfm_decision_sweep():
+    """ensembles.cc:513-521 adds cfm when the JacobiSVD condition number of J M^-1 J^T reaches 1e7
+    (utils.cc:256-287).  The device decides from a pivoted LDL^T plus power / inverse iteration
+    (egg_dense.cu).  Sweep: two separate boxes, each resting on ONE vertex (3 rows each), the second
+    one heavier by a factor mu, so that cond(A) ~ mu x cond(one box); mu is bisected on the oracle
+    until cond crosses 1e7 and the two decisions are compared on a ladder of relative offsets
+    around the crossing.  They must agree wherever |cond / 1e7 - 1| > 1e-6; the printout shows the
+    closest offsets and both decisions."""
+    import eggshell_b200 as E
+    from oracle import pyoracle as O
+    q = np.random.default_rng(77).normal(size=(2, 4))
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    Rm = E.scenes.quat_to_mat(q)
+
+    def scene_for(mus):
+        W = len(mus)
+        sc = E.scenes.cairn(W, rocks=2, seed=5)
+        sc["R"][:] = Rm[None]
+        sc["v"][:] = 0.0; sc["w"][:] = 0.0
+        corners = np.array([[sx, sy, sz] for sx in (-.15, .15) for sy in (-.15, .15) for sz in (-.15, .15)])
+        for k in range(2):
+            low = np.sort((corners @ Rm[k].T)[:, 2])
+            assert low[1] - low[0] > 5e-3                       # exactly one vertex below the ground
+            sc["p"][:, k, :] = (2.0 * k, 0.0, -low[0] - 1e-3)
+        sc["m"][:, 1] = mus
+        sc["I"][:, 1] = np.eye(3)[None] * (0.1 * np.asarray(mus))[:, None, None]
+        return sc
+
+    def oracle_cond(sc, w):
+        ow, _ = oracle_world(sc, w, solver=0)
+        ow.update_contacts()
+        assert ow.n_contacts == 2
+        return O.condition_number(ow.dense_A(0.0))
+
+    lo, hi = 1e5, 1e9
+    for _ in range(60):
+        mid = np.sqrt(lo * hi)
+        if oracle_cond(scene_for([mid]), 0) < 1e7: lo = mid
+        else: hi = mid
+    mu_star = np.sqrt(lo * hi)
+    offs = np.concatenate([-(10.0 ** -np.arange(1, 10)), [0.0], 10.0 ** -np.arange(9, 0, -1)])
+    offs = np.concatenate([[-0.9, -0.5], offs, [0.5, 9.0, 99.0]])
+    mus = mu_star * (1.0 + offs)
+    sc = scene_for(mus)
+    b = E.scenes.make_batch(sc, solver=E.SOLVER_DENSE_MURTY)
+    b.step(sc["dt"])
+    dev = b.status()["cfm_applied"].copy()
+    b.close()
+    rows = []
+    for w, off in enumerate(offs):
+        c = oracle_cond(sc, w)
+        ref = int(not (c < 1e7))
+        rows.append((off, c, ref, int(dev[w])))
+        if abs(c / 1e7 - 1.0) > 1e-6:
+            assert ref == dev[w], f"cfm decision differs at cond = {c:.9e} (offset {off:+.1e}): oracle {ref}, device {dev[w]}"
+    assert {r[2] for r in rows} == {0, 1}
+    print("cfm decision sweep around cond = 1e7 (offset, oracle cond, oracle decision, device decision):")
+    for r in rows:
+        print("  %+.1e  %.12e  %d  %d%s" % (r[0], r[1], r[2], r[3], "" if r[2] == r[3] else "   <-- differ"))
+
+
+def test_post_stabilize_matches_oracle():
+    """Row f1, second half: Ensemble::PostStabilize (ensembles.cc:624-657).  A hanging chain whose
+    joints are broken by ~1 cm is stabilised one StepPostStabilization at a time from shared state
+    (positions AND velocities move), then in one call to the end."""
+    import eggshell_b200 as E
+    rng = np.random.default_rng(9)
+    chain = E.scenes.chain(5, links=6, anchor=(0.0, 0.0, 3.0))
+    chain["p"] += rng.uniform(-0.01, 0.01, size=chain["p"].shape)
+    chain["v"] = rng.uniform(-0.1, 0.1, size=chain["v"].shape)
+    W = chain["W"]
+    b = E.Batch(W, chain["n"], chain["nj"], solver=E.SOLVER_PGS)
+    b.set_bodies(chain["p"], chain["R"], chain["v"], chain["w"], chain["m"], chain["I"])
+    b.set_joints(chain["i0"], chain["i1"], chain["c0"], chain["c1"])
+    b.init()                                    # BAD_INIT expected: the joints are broken on purpose
+    ows = [oracle_world(chain, wi, solver=1)[0] for wi in range(W)]
+    total = 0
+    for it in range(6):
+        p0, R0, v0, w0 = b.bodies()
+        steps, e2 = b.post_stabilize(max_steps=1)
+        p, R, v, w = b.bodies()
+        for wi, ow in enumerate(ows):
+            ow.set_state(p0[wi], R0[wi], v0[wi], w0[wi])
+            osteps, oe2 = ow.post_stabilize(max_steps=1)
+            assert steps[wi] == osteps
+            op, oR, ov, owv = ow.bodies()
+            for key, a, c in (("p", p[wi], op), ("R", R[wi], oR), ("v", v[wi], ov), ("w", w[wi], owv)):
+                assert rel_err(a, c, SCALE[key]) <= 1e-9, (it, wi, key, rel_err(a, c, SCALE[key]))
+            total += osteps
+    assert total > 10
+    steps, e2 = b.post_stabilize()
+    assert np.all((e2 <= 1e-9) | (steps == 500))
+    b.close()
+
+
+def test_contacts_range_matches_full_readback():
+    """egg_get_contacts_range: device-side transposes, any world range."""
+    import eggshell_b200 as E
+    scene = E.scenes.pile64(9, seed=3000)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=5)
+    b.step(scene["dt"])
+    full = b.contacts()
+    part = b.contacts(first=3, n_worlds=4)
+    for k in full:
+        assert np.array_equal(full[k][3:7], part[k]), k
+    assert full["count"].min() > 300
+    b.close()
 
 
 def test_broadphase_cull_keeps_pair_list():
@@ -454,7 +611,7 @@ def test_cpp_host_mirror_demo():
     for _ in range(25):
         W.step(0.001)
     p, R, v, w = W.bodies()
-    assert rel_err(got[:, :3], p) <= 1e-9 and rel_err(got[:, 3:], v, floor=1e-3) <= 1e-6
+    assert rel_err(got[:, :3], p, SCALE["p"]) <= 1e-9 and rel_err(got[:, 3:], v, SCALE["v"]) <= 1e-9
     j = lines.index("cairn 4")
     cairn = np.array([[float(x) for x in ln.split()[1:]] for ln in lines[j + 1:j + 5]])
     assert np.all(cairn[:, 5] < 0)      # the rocks are falling
@@ -481,11 +638,10 @@ def test_jacobi_sor_stepwise(solver, name):
             b.step(scene["dt"])
             for ow in ows:
                 ow.step(scene["dt"])
-            worst = compare_step(b, ows, idx, tol=1e-8)
+            worst = compare_step(b, ows, idx, tol=1e-9)
             st = b.status()
             for k, wi in enumerate(idx):
                 assert st["sweeps"][wi] == ows[k].stats()["sweeps"], (name, scene["name"], s, wi)
-            assert worst["lam"] <= 1e-6, (name, scene["name"], worst)
         b.close()
 
 
@@ -531,7 +687,7 @@ def test_init_stabilize_matches_oracle():
                 osteps, oe2 = ow.init_stabilize(max_steps=1)
                 assert steps[wi] == osteps, (scene["name"], it, wi, steps[wi], osteps)
                 op, oR, _, _ = ow.bodies()
-                assert rel_err(p[wi], op) <= 1e-8 and rel_err(R[wi], oR) <= 1e-8, (scene["name"], it, wi, rel_err(p[wi], op), rel_err(R[wi], oR))
+                assert rel_err(p[wi], op, SCALE["p"]) <= 1e-8 and rel_err(R[wi], oR, SCALE["R"]) <= 1e-8, (scene["name"], it, wi, rel_err(p[wi], op, SCALE["p"]), rel_err(R[wi], oR, SCALE["R"]))
                 assert con["count"][wi] == ow.n_contacts
                 total += osteps
         b.close()
