@@ -216,6 +216,10 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   b->stage_bytes = (size_t)W * n * 9 * sizeof(double);
   size_t jb = (size_t)W * (nj > 0 ? nj : 1) * 3 * sizeof(double);
   if (jb > b->stage_bytes) b->stage_bytes = jb;
+  {   // the contact taps are transposed through the same buffer: room for the geometry of up to 256 worlds at a time
+    const size_t cb = (size_t)(W < 256 ? W : 256) * maxc * 3 * sizeof(double);
+    if (cb > b->stage_bytes) b->stage_bytes = cb;
+  }
   DA(b->stage, b->stage_bytes / sizeof(double));
   // Shared-memory needs of every kernel this batch can launch, against the device limit: an
   // unsupported shape fails here, not as a launch error inside the first egg_step.
@@ -404,7 +408,8 @@ int egg_init(egg_batch* b) {
   // conflict scan lives in the narrowphase kernel, so run it once here -- EGG_ST_JOINT_CONFLICT is
   // then visible right after egg_init, as the reference's Panic would be.
   LK(egg_launch_collide(b->dev, b->stream));
-  b->launches++;
+  LK(egg_launch_clear_contacts(b->dev, b->stream));   // the contact list stays empty until the first Step / UpdateContacts, as in the reference
+  b->launches += 2;
   b->initialised = true;
   b->iso_known = false;
   return EGG_OK;

@@ -63,8 +63,11 @@ struct DenseCfg {
   size_t smem;             // dynamic shared memory bytes
 };
 
+constexpr int PB = 4;     // columns per panel of the factorisation
+
 struct Sm {
-  double *x, *w, *bx, *bw, *rhs, *xs, *tmp;   // [Rcap] each
+  double *x, *w, *bx, *bw, *rhs, *xs;          // [Rcap] each
+  double* tmp;                                 // [PB Rcap] scratch (panel temporaries of the factorisation; [Rcap] elsewhere)
   double* F;                                   // [Fcap] packed factor
   double* sa;                                  // [6 n] a = M^-1 J^T lambda
   unsigned short *sidx, *perm;                 // [Rcap]
@@ -77,7 +80,7 @@ __device__ Sm carve(unsigned char* raw, const DenseCfg& c, int n) {
   Sm s;
   double* p = reinterpret_cast<double*>(raw);
   s.x = p; p += c.Rcap; s.w = p; p += c.Rcap; s.bx = p; p += c.Rcap; s.bw = p; p += c.Rcap;
-  s.rhs = p; p += c.Rcap; s.xs = p; p += c.Rcap; s.tmp = p; p += c.Rcap;
+  s.rhs = p; p += c.Rcap; s.xs = p; p += c.Rcap; s.tmp = p; p += (size_t)PB * c.Rcap;
   s.sa = p; p += 6 * n;
   s.F = p; p += c.Fcap;
   s.sidx = reinterpret_cast<unsigned short*>(p);
@@ -160,10 +163,12 @@ __device__ void order_by_diag(double* dabs, int k, unsigned short* perm) {
 // from M's LOWER triangle, exactly as Eigen's in-place swaps do (orc::LDLT::compute).
 __device__ void ldlt_gather(const double* __restrict__ M, int ld, const unsigned short* idx, const unsigned short* perm, int k, double* F) {
   const int total = (int)tri(k);
+  // entries are independent: four loads in flight per thread (the source is L2-resident, ~700 cycles away)
+#pragma unroll 4
   for (int e = threadIdx.x; e < total; e += DT) {
     int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-    while ((int)tri(i + 1) <= e) i++;
-    while ((int)tri(i) > e) i--;
+    i += ((int)tri(i + 1) <= e) ? 1 : 0;       // the float estimate is off by at most one either way
+    i -= ((int)tri(i) > e) ? 1 : 0;
     const int j = e - (int)tri(i);
     int a = perm[i], b = perm[j];
     if (idx) { a = idx[a]; b = idx[b]; }
@@ -174,10 +179,114 @@ __device__ void ldlt_gather(const double* __restrict__ M, int ld, const unsigned
 }
 
 // In-place left-looking factorisation of the packed lower triangle F (k x k): on exit F holds L
-// strictly below the diagonal and D on it; tmp[k] is scratch.  Per entry: t = sum_j L[i][j] *
-// (D[j] L[kk][j]) for ascending j from 0, then A[i][kk] - t, then / D[kk]: orc::LDLT::compute.
-// Two barriers per column.
-__device__ void ldlt_factor(double* F, int k, double* tmp) {
+// strictly below the diagonal and D on it.  Per entry: t = sum_j L[i][j] * (D[j] L[kk][j]) for
+// ascending j from 0 in one accumulator, then A[i][kk] - t, then / D[kk]: orc::LDLT::compute.
+//
+// The dot product of an entry is a serial chain, so the columns are processed in panels of PB: a
+// thread that owns row i carries the PB accumulators of its panel entries through
+//   B. the terms j < c0 (finished columns): PB independent chains that share the L[i][j] load,
+//   C. the terms inside the panel: warp 0 finishes the PB x PB diagonal block with shuffles (it owns
+//      those rows) and publishes D and the in-panel temporaries; the rows below then finish their
+//      PB entries on their own.
+// Three barriers per panel.  T = scratch [PB][k] (temporaries D[j] L[c0+q][j], interleaved by j).
+__device__ void ldlt_factor(double* F, int k, double* T) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  __shared__ double s_D[PB];              // pivots of the panel columns
+  __shared__ double s_tin[PB][PB];        // in-panel temporaries: s_tin[q][q2] = D[c0+q2] L[c0+q][c0+q2], q2 < q
+  __shared__ int s_stop;
+  constexpr int RPT = 2;                  // rows per thread: k <= RPT * DT (the caller guarantees it)
+  if (tid == 0) s_stop = 0;
+  for (int c0 = 0; c0 < k; c0 += PB) {
+    const int nb = (k - c0 < PB) ? k - c0 : PB;
+    // A. temporaries of the finished columns for the PB rows of the panel
+    for (int e = tid; e < PB * c0; e += DT) {
+      const int j = e / PB, q = e - j * PB;
+      T[e] = (q < nb) ? F[tri(j) + j] * F[tri(c0 + q) + j] : 0.0;
+    }
+    __syncthreads();
+    // B. partial dot products over j < c0
+    double acc[RPT][PB];
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+#pragma unroll
+      for (int q = 0; q < PB; q++) acc[r][q] = 0.0;
+      const int i = c0 + tid + r * DT;
+      if (i < k) {
+        const double* ri = F + tri(i);
+        for (int j = 0; j < c0; j++) {
+          const double f = ri[j];
+          const double* tj = T + (size_t)j * PB;
+#pragma unroll
+          for (int q = 0; q < PB; q++) { const double pr = f * tj[q]; acc[r][q] += pr; }
+        }
+      }
+    }
+    // C1. the diagonal block: rows c0 .. c0+nb-1 are lanes 0 .. nb-1 of warp 0 (r = 0)
+    if (tid < 32) {
+      double myf[PB];                     // this lane's finished entries F[c0+lane][c0+q], q < lane
+      double Dq[PB];
+#pragma unroll
+      for (int q = 0; q < PB; q++) { myf[q] = 0.0; Dq[q] = 0.0; }
+#pragma unroll
+      for (int q = 0; q < PB; q++) {
+        if (q < nb) {
+          // finish column c0+q for the block rows l >= q: terms q2 < q use row (c0+q)'s entries, held by lane q
+          double t = acc[0][q];
+#pragma unroll
+          for (int q2 = 0; q2 < PB; q2++) {
+            if (q2 < q) {
+              const double tin = __shfl_sync(FULL, Dq[q2] * myf[q2], q);     // D[c0+q2] L[c0+q][c0+q2]
+              const double pr = myf[q2] * tin;
+              t += pr;
+              if (lane == q) s_tin[q][q2] = tin;
+            }
+          }
+          double val = 0.0;
+          if (lane >= q && lane < nb) val = F[tri(c0 + lane) + c0 + q] - t;
+          const double akk = __shfl_sync(FULL, val, q);
+          const bool valid = fabs(akk) > 0;
+          Dq[q] = akk;
+          if (lane == q) { F[tri(c0 + q) + c0 + q] = val; s_D[q] = akk; if (c0 + q == 0 && !valid) s_stop = 1; }
+          if (lane > q && lane < nb) {
+            if (valid) val /= akk;
+            F[tri(c0 + lane) + c0 + q] = val;
+            myf[q] = val;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (s_stop) break;                     // orc::LDLT::compute: first pivot zero, matrix left as it is
+    // C2. the rows below the block finish their panel entries on their own
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+      const int i = c0 + tid + r * DT;
+      if (i < k && i >= c0 + nb) {
+        double* ri = F + tri(i);
+        double myf[PB];
+#pragma unroll
+        for (int q = 0; q < PB; q++) {
+          if (q < nb) {
+            double t = acc[r][q];
+#pragma unroll
+            for (int q2 = 0; q2 < PB; q2++)
+              if (q2 < q) { const double pr = myf[q2] * s_tin[q][q2]; t += pr; }
+            double val = ri[c0 + q] - t;
+            const double akk = s_D[q];
+            if (fabs(akk) > 0) val /= akk;
+            ri[c0 + q] = val;
+            myf[q] = val;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
+// The plain column-by-column form of the same factorisation (any k; two barriers per column).
+__device__ void ldlt_factor_columns(double* F, int k, double* tmp) {
   const int tid = threadIdx.x;
   for (int kk = 0; kk < k; kk++) {
     const double* rk = F + tri(kk);
@@ -188,12 +297,7 @@ __device__ void ldlt_factor(double* F, int k, double* tmp) {
       for (int i = kk + tid; i < k; i += DT) {
         const double* ri = F + tri(i);
         double t = 0;
-        int j = 0;
-        for (; j + 4 <= kk; j += 4) {
-          const double a0 = ri[j] * tmp[j], a1 = ri[j + 1] * tmp[j + 1], a2 = ri[j + 2] * tmp[j + 2], a3 = ri[j + 3] * tmp[j + 3];
-          t += a0; t += a1; t += a2; t += a3;
-        }
-        for (; j < kk; j++) t += ri[j] * tmp[j];
+        for (int j = 0; j < kk; j++) { const double pr = ri[j] * tmp[j]; t += pr; }
         F[tri(i) + kk] -= t;
       }
       __syncthreads();
@@ -212,27 +316,111 @@ __device__ void ldlt_factor(double* F, int k, double* tmp) {
 }
 
 // x <- L^-T D^+ L^-1 x for x in PIVOTED order (x[pos] belongs to element perm[pos]); the caller
-// applies the transpositions by gathering / scattering through perm.  orc::LDLT::solve: forward
-// row i receives its terms for ascending j, the backward sweep is the column form.
+// applies the transpositions by gathering / scattering through perm.  orc::LDLT::solve: forward,
+// row i receives its terms for ascending j; the backward sweep is the column form (descending j).
+// Every thread keeps its rows' running values in registers; the unknowns are resolved in panels
+// of PB: the warp that owns the panel's rows solves the PB x PB triangle with shuffles and
+// publishes the values, everybody else applies the PB terms in order.  One barrier per panel.
 __device__ void ldlt_solve(const double* F, int k, double* x) {
-  const int tid = threadIdx.x;
-  for (int j = 0; j + 1 < k; j++) {
-    const double xj = x[j];
-    for (int i = j + 1 + tid; i < k; i += DT) x[i] -= F[tri(i) + j] * xj;
+  const int tid = threadIdx.x, lane = tid & 31;
+  constexpr int RPT = 2;                      // k <= RPT * DT, as in ldlt_factor
+  if (k > RPT * DT) {                         // plain form: one barrier per unknown
+    for (int j = 0; j + 1 < k; j++) {
+      const double xj = x[j];
+      for (int i = j + 1 + tid; i < k; i += DT) x[i] -= F[tri(i) + j] * xj;
+      __syncthreads();
+    }
+    const double tol0 = 1.0 / 1.7976931348623157e308;
+    for (int i = tid; i < k; i += DT) { const double dd = F[tri(i) + i]; x[i] = (fabs(dd) > tol0) ? x[i] / dd : 0.0; }
     __syncthreads();
+    for (int j = k - 1; j >= 1; j--) {
+      const double xj = x[j];
+      const double* rj = F + tri(j);
+      for (int i = tid; i < j; i += DT) x[i] -= rj[i] * xj;
+      __syncthreads();
+    }
+    return;
   }
+  double xr[RPT];
+#pragma unroll
+  for (int r = 0; r < RPT; r++) { const int i = tid + r * DT; xr[r] = (i < k) ? x[i] : 0.0; }
+  __syncthreads();
+  // ---- L^-1 ----
+  for (int c0 = 0; c0 < k; c0 += PB) {
+    const int nb = (k - c0 < PB) ? k - c0 : PB;
+    const int ro = c0 / DT;                   // which of this thread's rows the panel rows are (all PB rows: same r, same warp)
+    const int t0 = c0 - ro * DT;              // thread that owns row c0
+    if ((tid >> 5) == (t0 >> 5)) {
+      const int l0 = t0 & 31;
+#pragma unroll
+      for (int r = 0; r < RPT; r++) {
+        if (r == ro) {
+#pragma unroll
+          for (int q = 0; q < PB; q++) {
+            if (q < nb) {
+              const double xq = __shfl_sync(FULL, xr[r], l0 + q);
+              const int me = lane - l0;       // my row is c0 + me
+              if (me > q && me < nb) { const double pr = F[tri(c0 + me) + c0 + q] * xq; xr[r] -= pr; }
+              if (me == q) x[c0 + q] = xq;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+      const int i = tid + r * DT;
+      if (i >= c0 + nb && i < k) {
+        const double* ri = F + tri(i) + c0;
+#pragma unroll
+        for (int q = 0; q < PB; q++)
+          if (q < nb) { const double pr = ri[q] * x[c0 + q]; xr[r] -= pr; }
+      }
+    }
+  }
+  // ---- D^+ ----
   const double tol = 1.0 / 1.7976931348623157e308;
-  for (int i = tid; i < k; i += DT) {
-    const double dd = F[tri(i) + i];
-    x[i] = (fabs(dd) > tol) ? x[i] / dd : 0.0;
+#pragma unroll
+  for (int r = 0; r < RPT; r++) {
+    const int i = tid + r * DT;
+    if (i < k) { const double dd = F[tri(i) + i]; xr[r] = (fabs(dd) > tol) ? xr[r] / dd : 0.0; }
+  }
+  // ---- L^-T, panels from the bottom ----
+  const int last = ((k - 1) / PB) * PB;
+  for (int c0 = last; c0 >= 0; c0 -= PB) {
+    const int nb = (k - c0 < PB) ? k - c0 : PB;
+    const int ro = c0 / DT;
+    const int t0 = c0 - ro * DT;
+    if ((tid >> 5) == (t0 >> 5)) {
+      const int l0 = t0 & 31;
+#pragma unroll
+      for (int r = 0; r < RPT; r++) {
+        if (r == ro) {
+#pragma unroll
+          for (int q = PB - 1; q >= 0; q--) {
+            if (q < nb) {
+              const double xq = __shfl_sync(FULL, xr[r], l0 + q);
+              const int me = lane - l0;
+              if (me >= 0 && me < q) { const double pr = F[tri(c0 + q) + c0 + me] * xq; xr[r] -= pr; }
+              if (me == q) x[c0 + q] = xq;
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RPT; r++) {
+      const int i = tid + r * DT;
+      if (i < c0) {
+#pragma unroll
+        for (int q = PB - 1; q >= 0; q--)
+          if (q < nb) { const double pr = F[tri(c0 + q) + i] * x[c0 + q]; xr[r] -= pr; }
+      }
+    }
   }
   __syncthreads();
-  for (int j = k - 1; j >= 1; j--) {
-    const double xj = x[j];
-    const double* rj = F + tri(j);
-    for (int i = tid; i < j; i += DT) x[i] -= rj[i] * xj;
-    __syncthreads();
-  }
 }
 
 // Factor the k x k block of M selected by idx (ascending element list, or nullptr) into Fuse
@@ -247,7 +435,8 @@ __device__ double* ldlt_block(const double* M, int ld, const unsigned short* idx
   __syncthreads();
   double* F = ((size_t)tri(k) <= (size_t)cfg.Fcap) ? sm.F : Fg;
   ldlt_gather(M, ld, idx, sm.perm, k, F);
-  ldlt_factor(F, k, sm.tmp);
+  if (k <= 2 * DT) ldlt_factor(F, k, sm.tmp);
+  else ldlt_factor_columns(F, k, sm.tmp);
   return F;
 }
 
@@ -658,14 +847,25 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
       if (d.prm.cfm_mode == 1) good = false;
       else if (d.prm.cfm_mode == 2) good = true;
       else {
-        for (int e = tid; e < R * R; e += DT) Wk[e] = A[e];
-        __syncthreads();
-        work += (double)R * R * R / 3.0;
-        double lb = 0;
-        good = pivoted_ldlt_range(Wk, R, piv, &lb) != 0;
-        __syncthreads();
-        if (good && lb >= 1e4) good = cond_refine_is_good(A, Wk, R, piv, sm.x, sm.w, sm.xs, s_red);
-        __syncthreads();
+        // Two contacts between the same two bodies (or of one body with the ground) make J rank
+        // deficient whatever else is in the world: the 6 rows only see the relative twist, and the
+        // relative velocities of two points of a rigid motion differ by w x (p2 - p1), which has no
+        // component along p2 - p1.  Then A = J M^-1 J^T is singular, the SVD condition number is
+        // ~1e16 or inf (far beyond 1e7) and cfm is added: no factorisation needed.  Contacts of one
+        // pair are consecutive in the list (ensembles.cc:449-473).
+        int twin = 0;
+        for (int c = nj + tid; c + 1 < nc; c += DT) twin |= (ci0[c] == ci0[c + 1]) && (ci1[c] == ci1[c + 1]);
+        work += (double)R * R * R / 3.0;               // the reference's decision costs this much (and more) either way
+        if (__syncthreads_or(twin)) good = false;
+        else {
+          for (int e = tid; e < R * R; e += DT) Wk[e] = A[e];
+          __syncthreads();
+          double lb = 0;
+          good = pivoted_ldlt_range(Wk, R, piv, &lb) != 0;
+          __syncthreads();
+          if (good && lb >= 1e4) good = cond_refine_is_good(A, Wk, R, piv, sm.x, sm.w, sm.xs, s_red);
+          __syncthreads();
+        }
       }
       if (!good) {
         for (int i = tid; i < R; i += DT) A[(size_t)i * R + i] += d.prm.cfm;
@@ -808,14 +1008,49 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
           for (int i = tid; i < I; i += DT)
             if (!sm.S[i]) sm.x[i] = sm.athi[i] ? row_hi(i, boxed) : row_lo(i, boxed);
           __syncthreads();
-          for (int i = tid; i < I; i += DT) {
-            if (sm.S[i]) { sm.w[i] = 0.0; continue; }
-            const double* Li = Lm + (size_t)i * I;
-            double s2 = 0;
-            for (int k = 0; k < ks; k++) { const int g = sm.sidx[k]; s2 += Li[g] * sm.x[g]; }
-            sm.w[i] = s2 - sm.rhs[i];
+          // w_N = A_NS x_S - b_N (lcp.cc:219-226): row i sums A(i, j) x(j) over the basic j in ascending
+          // order.  The products are formed by all threads (independent, coalesced L2 loads: nothing
+          // waits on the sum) into the free tail of the factor storage, chunk by chunk; one thread
+          // per non-basic row then adds its chunk in order.
+          {
+            const int nn = build_index_list(sm.S, 0, I, sm.perm);      // non-basic rows, ascending (perm is free again)
+            double* P = sm.F + (((size_t)tri(ks) <= (size_t)cfg.Fcap) ? tri(ks) : 0);
+            const int room = cfg.Fcap - (int)(P - sm.F);
+            int cw = nn > 0 ? room / nn : ks;                           // basic columns per chunk
+            if (cw > ks) cw = ks;
+            for (int q = tid; q < nn; q += DT) sm.tmp[q] = 0.0;        // running sums
+            for (int i = tid; i < I; i += DT) if (sm.S[i]) sm.w[i] = 0.0;
+            __syncthreads();
+            if (cw >= 8) {
+              for (int k0 = 0; k0 < ks; k0 += cw) {
+                const int kc = (ks - k0 < cw) ? ks - k0 : cw;
+#pragma unroll 4
+                for (int e = tid; e < nn * kc; e += DT) {
+                  const int q = e / kc, k = e - q * kc;
+                  const int g = sm.sidx[k0 + k];
+                  P[e] = Lm[(size_t)sm.perm[q] * I + g] * sm.x[g];
+                }
+                __syncthreads();
+                for (int q = tid; q < nn; q += DT) {
+                  double s2 = sm.tmp[q];
+                  const double* pq = P + (size_t)q * kc;
+                  for (int k = 0; k < kc; k++) s2 += pq[k];
+                  sm.tmp[q] = s2;
+                }
+                __syncthreads();
+              }
+            } else {                                                    // no room to stage products: thread per row
+              for (int q = tid; q < nn; q += DT) {
+                const double* Li = Lm + (size_t)sm.perm[q] * I;
+                double s2 = 0;
+                for (int k = 0; k < ks; k++) { const int g = sm.sidx[k]; s2 += Li[g] * sm.x[g]; }
+                sm.tmp[q] = s2;
+              }
+              __syncthreads();
+            }
+            for (int q = tid; q < nn; q += DT) { const int i = sm.perm[q]; sm.w[i] = sm.tmp[q] - sm.rhs[i]; }
+            __syncthreads();
           }
-          __syncthreads();
           // UpdatePreviousBestSolution (lcp.cc:127-137)
           int differs = 0;
           for (int i = tid; i < I; i += DT) differs |= (sm.x[i] != sm.bx[i]) || (sm.w[i] != sm.bw[i]);
@@ -1064,9 +1299,9 @@ static DenseCfg dense_cfg(const EggDev& d) {
   c.off_vec = take(2 * R);
   c.off_int = take((size_t)c.ncap + (R + 3) / 4 + 2);      // 2 ncap ints + Rcap u16
   c.per_cta = o;
-  // shared memory: 7 vectors, 6 n accumulator, index lists and masks; the rest of the per-CTA
+  // shared memory: 6 vectors + the panel scratch, 6 n accumulator, index lists and masks; the rest of the per-CTA
   // budget (two CTAs per SM) is the packed factor
-  const size_t fixed = (7 * R + 6 * (size_t)d.n) * sizeof(double) + R * (2 * sizeof(unsigned short) + 2) + 64;
+  const size_t fixed = ((6 + PB) * R + 6 * (size_t)d.n) * sizeof(double) + R * (2 * sizeof(unsigned short) + 2) + 64;
   const char* e = getenv("EGG_DENSE_SMEM_KB");
   size_t budget = (size_t)(e ? atoi(e) : 111) * 1024;
   if (budget > 225 * 1024) budget = 225 * 1024;

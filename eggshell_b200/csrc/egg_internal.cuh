@@ -131,6 +131,7 @@ __host__ __device__ inline double sign1(double a) { return (a >= 0) ? 1.0 : -1.0
 // EGG_ERR_CUDA with the wrapper's name in egg_last_error().
 cudaError_t egg_launch_collide(const EggDev& d, cudaStream_t s);
 cudaError_t egg_launch_init(const EggDev& d, cudaStream_t s);
+cudaError_t egg_launch_clear_contacts(const EggDev& d, cudaStream_t s);
 cudaError_t egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
 cudaError_t egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
 cudaError_t egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s);

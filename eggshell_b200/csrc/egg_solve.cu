@@ -119,6 +119,19 @@ __global__ void egg_init_check_kernel(EggDev d) {
   if (fabs(e.x) > 1e-9 || fabs(e.y) > 1e-9 || fabs(e.z) > 1e-9) atomicOr(&d.status[w], 4 /*EGG_ST_BAD_INIT*/);
 }
 
+// After the init-time narrowphase pass (run only for its joint-joint conflict scan): the reference's
+// contact list is empty until the first Step / UpdateContacts (Ensemble::Init never calls
+// UpdateContacts, ensembles.cc:24-29), so the list, its statistics and a contact-overflow flag of
+// that pass are dropped again.
+__global__ void egg_clear_contacts_kernel(EggDev d) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.W) return;
+  d.c_count[w] = 0;
+  int* st = d.stats + (size_t)w * 8;
+  st[0] = 0; st[1] = 0; st[2] = 3 * d.nj; st[3] = 0;
+  d.status[w] &= ~8;
+}
+
 __global__ void egg_cost_kernel(EggDev d, double* cost) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= d.W) return;
@@ -201,6 +214,11 @@ cudaError_t egg_launch_init(const EggDev& d, cudaStream_t s) {
   }
   EGG_FIRST(e, cudaGetLastError());
   return e;
+}
+
+cudaError_t egg_launch_clear_contacts(const EggDev& d, cudaStream_t s) {
+  egg_clear_contacts_kernel<<<(d.W + 127) / 128, 128, 0, s>>>(d);
+  return cudaGetLastError();
 }
 
 cudaError_t egg_launch_costs(const EggDev& d, double* cost_d, cudaStream_t s) {

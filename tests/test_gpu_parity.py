@@ -535,6 +535,32 @@ def test_post_stabilize_matches_oracle():
     steps, e2 = b.post_stabilize()
     assert np.all((e2 <= 1e-9) | (steps == 500))
     b.close()
+    # with contacts: rocks resting on one vertex; both sides take one Step (which leaves the contact
+    # list the loop keeps using, ensembles.cc:624-645), then stabilise one step at a time
+    rocks = E.scenes.cairn(16, rocks=2, xb=(-1.0, 1.0), yb=(-1.0, 1.0), zb=(0.235, 0.255), seed=43)
+    b = E.scenes.make_batch(rocks, solver=E.SOLVER_PGS)
+    ows = [oracle_world(rocks, wi, solver=1)[0] for wi in range(16)]
+    b.step(rocks["dt"])
+    for ow in ows:
+        ow.step(rocks["dt"])
+    ncon = b.contacts()["count"]
+    compared = 0
+    for it in range(3):
+        p0, R0, v0, w0 = b.bodies()
+        steps, e2 = b.post_stabilize(max_steps=1)
+        p, R, v, w = b.bodies()
+        for wi, ow in enumerate(ows):
+            if ncon[wi] != ow.n_contacts or ncon[wi] > 2:
+                continue                               # > 1 contact per rock: J J^T singular, see test_init_stabilize_matches_oracle
+            ow.set_state(p0[wi], R0[wi], v0[wi], w0[wi])
+            osteps, oe2 = ow.post_stabilize(max_steps=1)
+            assert steps[wi] == osteps
+            op, oR, ov, owv = ow.bodies()
+            for key, a, c in (("p", p[wi], op), ("R", R[wi], oR), ("v", v[wi], ov), ("w", w[wi], owv)):
+                assert rel_err(a, c, SCALE[key]) <= 1e-8, ("rocks", it, wi, key, rel_err(a, c, SCALE[key]))
+            compared += int(ncon[wi] > 0 and osteps > 0)
+    assert compared > 0
+    b.close()
 
 
 def test_contacts_range_matches_full_readback():
@@ -615,6 +641,29 @@ def test_cpp_host_mirror_demo():
     j = lines.index("cairn 4")
     cairn = np.array([[float(x) for x in ln.split()[1:]] for ln in lines[j + 1:j + 5]])
     assert np.all(cairn[:, 5] < 0)      # the rocks are falling
+
+
+def test_host_demo_batch_dump_and_replay(tmp_path):
+    """the headless W-world driver.  host_demo steps 64 hanging chains through the C
+    ABI, dumps the batch state, keeps stepping; a second process rebuilds the batch from the dump and
+    must arrive at the same state bit for bit (same checksum line).  The dump's world 0 is also
+    read back in text form."""
+    import os
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "eggshell_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s"])
+    exe = os.path.join(host, "host_demo")
+    dump = str(tmp_path / "chains.eggstate")
+    a = subprocess.run([exe, "batch", "64", "8", "40", dump], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stderr
+    assert "status_or 0" in a.stdout
+    r = subprocess.run([exe, "replay", dump, "40"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    ca = [ln for ln in a.stdout.splitlines() if ln.startswith("checksum")]
+    cr = [ln for ln in r.stdout.splitlines() if ln.startswith("checksum")]
+    assert ca and ca == cr, (ca, cr)
+    sh = subprocess.run([exe, "show", dump, "63"], capture_output=True, text=True, timeout=60)
+    assert sh.returncode == 0 and len(sh.stdout.splitlines()) == 9 and "step 40" in sh.stdout.splitlines()[0]
 
 
 # ---------------------------------------------------------------------------------------------
