@@ -23,7 +23,7 @@ ST_LCP_FAILED, ST_JOINT_CONFLICT, ST_BAD_INIT, ST_CONTACT_OVERFLOW, ST_NONFINITE
 EXPORTS = [
     "egg_desc_default", "egg_create", "egg_destroy", "egg_set_bodies", "egg_set_state", "egg_set_joints",
     "egg_set_external", "egg_init", "egg_init_stabilize", "egg_post_stabilize", "egg_step", "egg_snapshot", "egg_restore", "egg_update_contacts", "egg_get_static", "egg_get_bodies", "egg_get_contacts", "egg_get_contacts_range", "egg_get_pair_hits", "egg_get_pair_hits_range",
-    "egg_get_status", "egg_get_dense_work", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
+    "egg_get_status", "egg_get_dense_work", "egg_get_debug_counters", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
     "egg_launch_count", "egg_capacity", "egg_set_profiling", "egg_get_kernel_ms", "egg_fp64_peak_tflops", "egg_host_alloc", "egg_host_free", "egg_last_error", "egg_version",
 ]
 
@@ -241,6 +241,11 @@ class Batch:
         """FP64 operations of the reference algorithm on each world's last dense solve [W]."""
         out = np.zeros(self.W)
         _chk(lib().egg_get_dense_work(self.h, _p(out)), "egg_get_dense_work")
+        return out
+
+    def debug_counters(self, reset=True):
+        out = np.zeros(32, dtype=np.uint64)
+        _chk(lib().egg_get_debug_counters(self.h, _p(out), int(reset)), "egg_get_debug_counters")
         return out
 
     def rollout_costs(self, device_ptr):

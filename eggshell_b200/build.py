@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libeggshell_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = (["-DEGG_STREAM_CHECKS"] if os.environ.get("EGG_STREAM_CHECKS") else []) + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+COMMON = (["-DEGG_STREAM_CHECKS"] if os.environ.get("EGG_STREAM_CHECKS") else []) + (["-DEGG_DENSE_TIMING"] if os.environ.get("EGG_DENSE_TIMING") else []) + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 UNITS = [
     ("egg_collide.cu", ["-fmad=false"]),
     ("egg_solve.cu", []),

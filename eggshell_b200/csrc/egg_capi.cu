@@ -211,6 +211,7 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   DA(d.resid, W);
   DA(d.cost0, (size_t)W * 2);
   DA(d.work_ctr, 4);
+  DA(d.dbg, 32);
   DA(d.minv_iso, (size_t)W * (n + 1) * 2);
   DA(d.iso_flag, 1);
   b->stage_bytes = (size_t)W * n * 9 * sizeof(double);
@@ -686,6 +687,15 @@ int egg_get_status(egg_batch* b, int* status, int* stats, double* residual) {
   if (status) CK(cudaMemcpyAsync(status, b->dev.status, W * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   if (stats) CK(cudaMemcpyAsync(stats, b->dev.stats, W * 8 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
   if (residual) CK(cudaMemcpyAsync(residual, b->dev.resid, W * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  CK(cudaStreamSynchronize(b->stream));
+  return EGG_OK;
+}
+
+int egg_get_debug_counters(egg_batch* b, unsigned long long* out32, int reset) {
+  if (!b || !out32) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  CK(cudaMemcpyAsync(out32, b->dev.dbg, 32 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+  if (reset) CK(cudaMemsetAsync(b->dev.dbg, 0, 32 * sizeof(unsigned long long), b->stream));
   CK(cudaStreamSynchronize(b->stream));
   return EGG_OK;
 }

@@ -76,6 +76,18 @@ struct Sm {
 
 __device__ __forceinline__ size_t tri(int i) { return (size_t)i * (size_t)(i + 1) / 2; }
 
+// Phase timing for development builds (EGG_DENSE_TIMING=1 python -m eggshell_b200.build --force):
+// TICK(slot) charges the cycles since the previous TICK of this CTA to `slot`; the totals of all
+// CTAs land in EggDev::dbg (egg_get_debug_counters).  Compiled out otherwise.
+#ifdef EGG_DENSE_TIMING
+__shared__ long long s_prof_t0;
+__shared__ unsigned long long s_prof[32];
+#define TICK(slot) do { __syncthreads(); if (threadIdx.x == 0) { const long long t__ = clock64(); s_prof[slot] += (unsigned long long)(t__ - s_prof_t0); s_prof_t0 = t__; } } while (0)
+#else
+#define TICK(slot) do { } while (0)
+#endif
+enum { T_ROWS = 0, T_CFM, T_SCHUR, T_CHECK, T_INDEX, T_ORDER, T_GATHER, T_FACTOR, T_SOLVE, T_W, T_BEST, T_XE, T_OUT, T_FA, T_FB, T_FC1, T_FC2, T_SFWD, T_SBWD, T_COUNT };
+
 __device__ Sm carve(unsigned char* raw, const DenseCfg& c, int n) {
   Sm s;
   double* p = reinterpret_cast<double*>(raw);
@@ -158,70 +170,108 @@ __device__ void order_by_diag(double* dabs, int k, unsigned short* perm) {
 }
 
 // ---- packed LDL^T: gather, factor, solve ------------------------------------------------------
+// The factor lives in shared memory when it fits and in the CTA's global slab otherwise; the
+// routines are templates over a tiny accessor so that the shared-memory case compiles to ld.shared /
+// st.shared (through a generic pointer every access would be a generic LD/ST and count as a
+// long-scoreboard wait: profiles/r2c_dense_lines.txt).
+struct ShMem {
+  unsigned base;          // shared-space byte address of element 0
+  __device__ __forceinline__ double ld(int i) const {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(base + 8u * (unsigned)i) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st(int i, double v) const { asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + 8u * (unsigned)i), "d"(v) : "memory"); }
+};
+struct GlMem {
+  double* p;
+  __device__ __forceinline__ double ld(int i) const { return p[i]; }
+  __device__ __forceinline__ void st(int i, double v) const { p[i] = v; }
+};
+__device__ __forceinline__ ShMem shmem(const double* p) { ShMem m; m.base = (unsigned)__cvta_generic_to_shared(p); return m; }
+__device__ __forceinline__ int itri(int i) { return i * (i + 1) / 2; }
+
 // Source matrix M (row-major, leading dimension ld, global); element e of the block is row/column
 // idx[e] of M (idx == nullptr: e itself).  The factor of the symmetrically permuted block is built
 // from M's LOWER triangle, exactly as Eigen's in-place swaps do (orc::LDLT::compute).
-__device__ void ldlt_gather(const double* __restrict__ M, int ld, const unsigned short* idx, const unsigned short* perm, int k, double* F) {
-  const int total = (int)tri(k);
+template <class FM>
+__device__ void ldlt_gather(const double* __restrict__ M, int ld, const unsigned short* idx, const unsigned short* perm, int k, FM F) {
+  const int total = itri(k);
   // entries are independent: four loads in flight per thread (the source is L2-resident, ~700 cycles away)
 #pragma unroll 4
   for (int e = threadIdx.x; e < total; e += DT) {
     int i = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-    i += ((int)tri(i + 1) <= e) ? 1 : 0;       // the float estimate is off by at most one either way
-    i -= ((int)tri(i) > e) ? 1 : 0;
-    const int j = e - (int)tri(i);
+    i += (itri(i + 1) <= e) ? 1 : 0;          // the float estimate is off by at most one either way
+    i -= (itri(i) > e) ? 1 : 0;
+    const int j = e - itri(i);
     int a = perm[i], b = perm[j];
     if (idx) { a = idx[a]; b = idx[b]; }
     const int r = a > b ? a : b, c = a > b ? b : a;
-    F[e] = M[(size_t)r * ld + c];
+    F.st(e, M[(size_t)r * ld + c]);
   }
   __syncthreads();
 }
 
-// In-place left-looking factorisation of the packed lower triangle F (k x k): on exit F holds L
-// strictly below the diagonal and D on it.  Per entry: t = sum_j L[i][j] * (D[j] L[kk][j]) for
-// ascending j from 0 in one accumulator, then A[i][kk] - t, then / D[kk]: orc::LDLT::compute.
+// In-place left-looking factorisation of the packed lower triangle F (k x k, k <= 2 DT): on exit F
+// holds L strictly below the diagonal and D on it.  Per entry: t = sum_j fma(L[i][j], D[j] L[kk][j], t)
+// for ascending j from 0 in one accumulator, then A[i][kk] - t, then / D[kk]: orc::LDLT::compute.
 //
-// The dot product of an entry is a serial chain, so the columns are processed in panels of PB: a
-// thread that owns row i carries the PB accumulators of its panel entries through
-//   B. the terms j < c0 (finished columns): PB independent chains that share the L[i][j] load,
-//   C. the terms inside the panel: warp 0 finishes the PB x PB diagonal block with shuffles (it owns
-//      those rows) and publishes D and the in-panel temporaries; the rows below then finish their
-//      PB entries on their own.
-// Three barriers per panel.  T = scratch [PB][k] (temporaries D[j] L[c0+q][j], interleaved by j).
-__device__ void ldlt_factor(double* F, int k, double* T) {
+// The dot product of an entry is a serial chain, so the columns are processed in panels of PB:
+//   A. temporaries D[j] L[c0+q][j] of the finished columns j < c0 for the PB panel columns;
+//   B. the partial sums over j < c0 of every panel entry (i >= c0, q < PB): all chains of a panel
+//      have the same length c0, so they are dealt out evenly over ALL threads, two chains per
+//      thread at a time (rows do not belong to threads: with a row per thread the last warp would
+//      carry most of the work and the other schedulers would idle);
+//   C. the terms inside the panel: warp 0 finishes the PB x PB diagonal block with shuffles and
+//      publishes D and the in-panel temporaries; one thread per row below finishes its PB entries.
+// Four barriers per panel.  T = shared scratch [PB k]: temporaries [PB c0] then partial sums.
+template <class FM>
+__device__ void ldlt_factor(FM F, int k, ShMem T) {
   const int tid = threadIdx.x, lane = tid & 31;
   __shared__ double s_D[PB];              // pivots of the panel columns
   __shared__ double s_tin[PB][PB];        // in-panel temporaries: s_tin[q][q2] = D[c0+q2] L[c0+q][c0+q2], q2 < q
   __shared__ int s_stop;
-  constexpr int RPT = 2;                  // rows per thread: k <= RPT * DT (the caller guarantees it)
+  constexpr int RPT = 2;                  // rows per thread in phase C2: k <= RPT * DT
   if (tid == 0) s_stop = 0;
   for (int c0 = 0; c0 < k; c0 += PB) {
     const int nb = (k - c0 < PB) ? k - c0 : PB;
-    // A. temporaries of the finished columns for the PB rows of the panel
+    const int accb = PB * c0;             // partial sums start here in T
+    // A. temporaries
     for (int e = tid; e < PB * c0; e += DT) {
-      const int j = e / PB, q = e - j * PB;
-      T[e] = (q < nb) ? F[tri(j) + j] * F[tri(c0 + q) + j] : 0.0;
+      const int jj = e / PB, q = e - jj * PB;
+      T.st(e, (q < nb) ? F.ld(itri(jj) + jj) * F.ld(itri(c0 + q) + jj) : 0.0);
     }
     __syncthreads();
-    // B. partial dot products over j < c0
-    double acc[RPT][PB];
-#pragma unroll
-    for (int r = 0; r < RPT; r++) {
-#pragma unroll
-      for (int q = 0; q < PB; q++) acc[r][q] = 0.0;
-      const int i = c0 + tid + r * DT;
-      if (i < k) {
-        const double* ri = F + tri(i);
-        for (int j = 0; j < c0; j++) {
-          const double f = ri[j];
-          const double* tj = T + (size_t)j * PB;
-#pragma unroll
-          for (int q = 0; q < PB; q++) { const double pr = f * tj[q]; acc[r][q] += pr; }
-        }
+    TICK(T_FA);
+    // B. partial sums, two chains per thread at a time
+    const int ntask = (k - c0) * PB;
+    for (int t0 = tid; t0 < ntask; t0 += 2 * DT) {
+      const int t1 = t0 + DT;
+      const bool two = t1 < ntask;
+      const int r0 = itri(c0 + t0 / PB), q0 = t0 % PB;
+      const int r1 = two ? itri(c0 + t1 / PB) : r0, q1 = two ? t1 % PB : q0;
+      double s0 = 0.0, s1 = 0.0;
+      int jj = 0;
+      for (; jj + 4 <= c0; jj += 4) {
+        const double a0 = F.ld(r0 + jj), a1 = F.ld(r0 + jj + 1), a2 = F.ld(r0 + jj + 2), a3 = F.ld(r0 + jj + 3);
+        const double b0 = T.ld(jj * PB + q0), b1 = T.ld((jj + 1) * PB + q0), b2 = T.ld((jj + 2) * PB + q0), b3 = T.ld((jj + 3) * PB + q0);
+        const double c0v = F.ld(r1 + jj), c1 = F.ld(r1 + jj + 1), c2 = F.ld(r1 + jj + 2), c3 = F.ld(r1 + jj + 3);
+        const double d0 = T.ld(jj * PB + q1), d1 = T.ld((jj + 1) * PB + q1), d2 = T.ld((jj + 2) * PB + q1), d3 = T.ld((jj + 3) * PB + q1);
+        s0 = __fma_rn(a0, b0, s0); s1 = __fma_rn(c0v, d0, s1);
+        s0 = __fma_rn(a1, b1, s0); s1 = __fma_rn(c1, d1, s1);
+        s0 = __fma_rn(a2, b2, s0); s1 = __fma_rn(c2, d2, s1);
+        s0 = __fma_rn(a3, b3, s0); s1 = __fma_rn(c3, d3, s1);
       }
+      for (; jj < c0; jj++) {
+        s0 = __fma_rn(F.ld(r0 + jj), T.ld(jj * PB + q0), s0);
+        s1 = __fma_rn(F.ld(r1 + jj), T.ld(jj * PB + q1), s1);
+      }
+      T.st(accb + t0, s0);
+      if (two) T.st(accb + t1, s1);
     }
-    // C1. the diagonal block: rows c0 .. c0+nb-1 are lanes 0 .. nb-1 of warp 0 (r = 0)
+    __syncthreads();
+    TICK(T_FB);
+    // C1. the diagonal block: rows c0 .. c0+nb-1 on lanes 0 .. nb-1 of warp 0
     if (tid < 32) {
       double myf[PB];                     // this lane's finished entries F[c0+lane][c0+q], q < lane
       double Dq[PB];
@@ -231,83 +281,85 @@ __device__ void ldlt_factor(double* F, int k, double* T) {
       for (int q = 0; q < PB; q++) {
         if (q < nb) {
           // finish column c0+q for the block rows l >= q: terms q2 < q use row (c0+q)'s entries, held by lane q
-          double t = acc[0][q];
+          double t = (lane < nb) ? T.ld(accb + lane * PB + q) : 0.0;
 #pragma unroll
           for (int q2 = 0; q2 < PB; q2++) {
             if (q2 < q) {
               const double tin = __shfl_sync(FULL, Dq[q2] * myf[q2], q);     // D[c0+q2] L[c0+q][c0+q2]
-              const double pr = myf[q2] * tin;
-              t += pr;
+              t = __fma_rn(myf[q2], tin, t);
               if (lane == q) s_tin[q][q2] = tin;
             }
           }
           double val = 0.0;
-          if (lane >= q && lane < nb) val = F[tri(c0 + lane) + c0 + q] - t;
+          if (lane >= q && lane < nb) val = F.ld(itri(c0 + lane) + c0 + q) - t;
           const double akk = __shfl_sync(FULL, val, q);
           const bool valid = fabs(akk) > 0;
           Dq[q] = akk;
-          if (lane == q) { F[tri(c0 + q) + c0 + q] = val; s_D[q] = akk; if (c0 + q == 0 && !valid) s_stop = 1; }
+          if (lane == q) { F.st(itri(c0 + q) + c0 + q, val); s_D[q] = akk; if (c0 + q == 0 && !valid) s_stop = 1; }
           if (lane > q && lane < nb) {
             if (valid) val /= akk;
-            F[tri(c0 + lane) + c0 + q] = val;
+            F.st(itri(c0 + lane) + c0 + q, val);
             myf[q] = val;
           }
         }
       }
     }
     __syncthreads();
+    TICK(T_FC1);
     if (s_stop) break;                     // orc::LDLT::compute: first pivot zero, matrix left as it is
     // C2. the rows below the block finish their panel entries on their own
 #pragma unroll
     for (int r = 0; r < RPT; r++) {
-      const int i = c0 + tid + r * DT;
-      if (i < k && i >= c0 + nb) {
-        double* ri = F + tri(i);
+      const int i = c0 + nb + tid + r * DT;
+      if (i < k) {
+        const int rb = itri(i) + c0;
         double myf[PB];
 #pragma unroll
         for (int q = 0; q < PB; q++) {
           if (q < nb) {
-            double t = acc[r][q];
+            double t = T.ld(accb + (i - c0) * PB + q);
 #pragma unroll
             for (int q2 = 0; q2 < PB; q2++)
-              if (q2 < q) { const double pr = myf[q2] * s_tin[q][q2]; t += pr; }
-            double val = ri[c0 + q] - t;
+              if (q2 < q) t = __fma_rn(myf[q2], s_tin[q][q2], t);
+            double val = F.ld(rb + q) - t;
             const double akk = s_D[q];
             if (fabs(akk) > 0) val /= akk;
-            ri[c0 + q] = val;
+            F.st(rb + q, val);
             myf[q] = val;
           }
         }
       }
     }
     __syncthreads();
+    TICK(T_FC2);
   }
   __syncthreads();
 }
 
 // The plain column-by-column form of the same factorisation (any k; two barriers per column).
-__device__ void ldlt_factor_columns(double* F, int k, double* tmp) {
+template <class FM>
+__device__ void ldlt_factor_columns(FM F, int k, double* tmp) {
   const int tid = threadIdx.x;
   for (int kk = 0; kk < k; kk++) {
-    const double* rk = F + tri(kk);
+    const int rk = itri(kk);
     if (kk > 0) {
       // temp[j] = D[j] L[kk][j]; entry kk-1 was written by the thread that closed column kk-1 (below)
-      for (int j = tid; j < kk - 1; j += DT) tmp[j] = F[tri(j) + j] * rk[j];
+      for (int j = tid; j < kk - 1; j += DT) tmp[j] = F.ld(itri(j) + j) * F.ld(rk + j);
       __syncthreads();
       for (int i = kk + tid; i < k; i += DT) {
-        const double* ri = F + tri(i);
+        const int ri = itri(i);
         double t = 0;
-        for (int j = 0; j < kk; j++) { const double pr = ri[j] * tmp[j]; t += pr; }
-        F[tri(i) + kk] -= t;
+        for (int j = 0; j < kk; j++) t = __fma_rn(F.ld(ri + j), tmp[j], t);
+        F.st(ri + kk, F.ld(ri + kk) - t);
       }
       __syncthreads();
     }
-    const double akk = F[tri(kk) + kk];
+    const double akk = F.ld(rk + kk);
     const bool valid = fabs(akk) > 0;
     if (kk == 0 && !valid) break;                      // orc::LDLT::compute: matrix left as it is
     for (int i = kk + 1 + tid; i < k; i += DT) {
-      double v = F[tri(i) + kk];
-      if (valid) { v /= akk; F[tri(i) + kk] = v; }
+      double v = F.ld(itri(i) + kk);
+      if (valid) { v /= akk; F.st(itri(i) + kk, v); }
       if (i == kk + 1) tmp[kk] = akk * v;              // the temp entry of the next column that needs this division
     }
     // the barrier at the top of the next column orders these writes before their use
@@ -317,26 +369,28 @@ __device__ void ldlt_factor_columns(double* F, int k, double* tmp) {
 
 // x <- L^-T D^+ L^-1 x for x in PIVOTED order (x[pos] belongs to element perm[pos]); the caller
 // applies the transpositions by gathering / scattering through perm.  orc::LDLT::solve: forward,
-// row i receives its terms for ascending j; the backward sweep is the column form (descending j).
-// Every thread keeps its rows' running values in registers; the unknowns are resolved in panels
-// of PB: the warp that owns the panel's rows solves the PB x PB triangle with shuffles and
-// publishes the values, everybody else applies the PB terms in order.  One barrier per panel.
-__device__ void ldlt_solve(const double* F, int k, double* x) {
+// row i receives its terms for ascending j; the backward sweep is the column form (descending j);
+// every term is one fma(-L, x_j, x_i).  Every thread keeps its rows' running values in registers;
+// the unknowns are resolved in panels of PB: the warp that owns the panel's rows solves the
+// PB x PB triangle with shuffles and publishes the values, everybody else applies the PB terms in
+// order.  One barrier per panel.
+template <class FM>
+__device__ void ldlt_solve(FM F, int k, double* x) {
   const int tid = threadIdx.x, lane = tid & 31;
   constexpr int RPT = 2;                      // k <= RPT * DT, as in ldlt_factor
   if (k > RPT * DT) {                         // plain form: one barrier per unknown
     for (int j = 0; j + 1 < k; j++) {
       const double xj = x[j];
-      for (int i = j + 1 + tid; i < k; i += DT) x[i] -= F[tri(i) + j] * xj;
+      for (int i = j + 1 + tid; i < k; i += DT) x[i] = __fma_rn(-F.ld(itri(i) + j), xj, x[i]);
       __syncthreads();
     }
     const double tol0 = 1.0 / 1.7976931348623157e308;
-    for (int i = tid; i < k; i += DT) { const double dd = F[tri(i) + i]; x[i] = (fabs(dd) > tol0) ? x[i] / dd : 0.0; }
+    for (int i = tid; i < k; i += DT) { const double dd = F.ld(itri(i) + i); x[i] = (fabs(dd) > tol0) ? x[i] / dd : 0.0; }
     __syncthreads();
     for (int j = k - 1; j >= 1; j--) {
       const double xj = x[j];
-      const double* rj = F + tri(j);
-      for (int i = tid; i < j; i += DT) x[i] -= rj[i] * xj;
+      const int rj = itri(j);
+      for (int i = tid; i < j; i += DT) x[i] = __fma_rn(-F.ld(rj + i), xj, x[i]);
       __syncthreads();
     }
     return;
@@ -360,7 +414,7 @@ __device__ void ldlt_solve(const double* F, int k, double* x) {
             if (q < nb) {
               const double xq = __shfl_sync(FULL, xr[r], l0 + q);
               const int me = lane - l0;       // my row is c0 + me
-              if (me > q && me < nb) { const double pr = F[tri(c0 + me) + c0 + q] * xq; xr[r] -= pr; }
+              if (me > q && me < nb) xr[r] = __fma_rn(-F.ld(itri(c0 + me) + c0 + q), xq, xr[r]);
               if (me == q) x[c0 + q] = xq;
             }
           }
@@ -372,19 +426,20 @@ __device__ void ldlt_solve(const double* F, int k, double* x) {
     for (int r = 0; r < RPT; r++) {
       const int i = tid + r * DT;
       if (i >= c0 + nb && i < k) {
-        const double* ri = F + tri(i) + c0;
+        const int ri = itri(i) + c0;
 #pragma unroll
         for (int q = 0; q < PB; q++)
-          if (q < nb) { const double pr = ri[q] * x[c0 + q]; xr[r] -= pr; }
+          if (q < nb) xr[r] = __fma_rn(-F.ld(ri + q), x[c0 + q], xr[r]);
       }
     }
   }
+  TICK(T_SFWD);
   // ---- D^+ ----
   const double tol = 1.0 / 1.7976931348623157e308;
 #pragma unroll
   for (int r = 0; r < RPT; r++) {
     const int i = tid + r * DT;
-    if (i < k) { const double dd = F[tri(i) + i]; xr[r] = (fabs(dd) > tol) ? xr[r] / dd : 0.0; }
+    if (i < k) { const double dd = F.ld(itri(i) + i); xr[r] = (fabs(dd) > tol) ? xr[r] / dd : 0.0; }
   }
   // ---- L^-T, panels from the bottom ----
   const int last = ((k - 1) / PB) * PB;
@@ -402,7 +457,7 @@ __device__ void ldlt_solve(const double* F, int k, double* x) {
             if (q < nb) {
               const double xq = __shfl_sync(FULL, xr[r], l0 + q);
               const int me = lane - l0;
-              if (me >= 0 && me < q) { const double pr = F[tri(c0 + q) + c0 + me] * xq; xr[r] -= pr; }
+              if (me >= 0 && me < q) xr[r] = __fma_rn(-F.ld(itri(c0 + q) + c0 + me), xq, xr[r]);
               if (me == q) x[c0 + q] = xq;
             }
           }
@@ -416,16 +471,19 @@ __device__ void ldlt_solve(const double* F, int k, double* x) {
       if (i < c0) {
 #pragma unroll
         for (int q = PB - 1; q >= 0; q--)
-          if (q < nb) { const double pr = F[tri(c0 + q) + i] * x[c0 + q]; xr[r] -= pr; }
+          if (q < nb) xr[r] = __fma_rn(-F.ld(itri(c0 + q) + i), x[c0 + q], xr[r]);
       }
     }
   }
   __syncthreads();
+  TICK(T_SBWD);
 }
 
-// Factor the k x k block of M selected by idx (ascending element list, or nullptr) into Fuse
-// (shared if it fits, else the global slab) and return the storage used.  dabs / perm: shared [k].
-__device__ double* ldlt_block(const double* M, int ld, const unsigned short* idx, int k, const Sm& sm, const DenseCfg& cfg, double* Fg) {
+// Factor the k x k block of M selected by idx (ascending element list, or nullptr) -- in shared
+// memory if it fits, else in the CTA's global slab -- and solve for the right-hand side held in
+// pivoted order in sm.xs by the caller's `load` (called once the pivot order sm.perm is known).
+template <class Load>
+__device__ void ldlt_block_solve(const double* M, int ld, const unsigned short* idx, int k, const Sm& sm, const DenseCfg& cfg, double* Fg, Load load) {
   for (int e = threadIdx.x; e < k; e += DT) {
     const int g = idx ? idx[e] : e;
     sm.tmp[e] = fabs(M[(size_t)g * ld + g]);
@@ -433,11 +491,25 @@ __device__ double* ldlt_block(const double* M, int ld, const unsigned short* idx
   __syncthreads();
   order_by_diag(sm.tmp, k, sm.perm);
   __syncthreads();
-  double* F = ((size_t)tri(k) <= (size_t)cfg.Fcap) ? sm.F : Fg;
-  ldlt_gather(M, ld, idx, sm.perm, k, F);
-  if (k <= 2 * DT) ldlt_factor(F, k, sm.tmp);
-  else ldlt_factor_columns(F, k, sm.tmp);
-  return F;
+  TICK(T_ORDER);
+  load();
+  const ShMem T = shmem(sm.tmp);
+  if ((size_t)tri(k) <= (size_t)cfg.Fcap) {
+    const ShMem F = shmem(sm.F);
+    ldlt_gather(M, ld, idx, sm.perm, k, F);
+    TICK(T_GATHER);
+    if (k <= 2 * DT) ldlt_factor(F, k, T); else ldlt_factor_columns(F, k, sm.tmp);
+    TICK(T_FACTOR);
+    ldlt_solve(F, k, sm.xs);
+  } else {
+    GlMem F; F.p = Fg;
+    ldlt_gather(M, ld, idx, sm.perm, k, F);
+    TICK(T_GATHER);
+    if (k <= 2 * DT) ldlt_factor(F, k, T); else ldlt_factor_columns(F, k, sm.tmp);
+    TICK(T_FACTOR);
+    ldlt_solve(F, k, sm.xs);
+  }
+  TICK(T_SOLVE);
 }
 
 // ---- cfm decision ------------------------------------------------------------------------------
@@ -788,6 +860,10 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
     const int w = s_world;
     __syncthreads();
     if (w >= d.W) break;
+#ifdef EGG_DENSE_TIMING
+    if (tid == 0) { s_prof_t0 = clock64(); for (int q = 0; q < 32; q++) s_prof[q] = 0; }
+    __syncthreads();
+#endif
 
     const int nc = nj + d.c_count[w];
     int R = 3 * nc;
@@ -842,6 +918,7 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
       }
       __syncthreads();
 
+      TICK(T_ROWS);
       // ---- 3. cfm decision (ensembles.cc:513-521) ----
       bool good;
       if (d.prm.cfm_mode == 1) good = false;
@@ -873,6 +950,7 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
         __syncthreads();
       }
 
+      TICK(T_CFM);
       // ---- 4. Schur complement on the equality rows (lcp.cc:286-294); rows 0..E-1 are the joints ----
       if (I > 0) {
         if (E > 0) {
@@ -986,6 +1064,7 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
         }
         __syncthreads();
 
+        TICK(T_SCHUR);
         // ---- 5. Murty principal pivoting on (Lm, rhs) ----
         for (int i = tid; i < I; i += DT) { sm.S[i] = 1; sm.athi[i] = 0; sm.x[i] = 0.0; sm.w[i] = -sm.rhs[i]; sm.bx[i] = 0.0; sm.bw[i] = -sm.rhs[i]; }
         __syncthreads();
@@ -996,13 +1075,12 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
         int iter = 0;
         while (iter < max_it) {
           if (check_murty(Lm, I, sm, sm.x, sm.w, boxed, 0.0)) break;
+          TICK(T_CHECK);
           const int ks = build_index_list(sm.S, 1, I, sm.sidx);
+          TICK(T_INDEX);
           work += (double)ks * ks * ks / 3.0 + 2.0 * ks * ks + 2.0 * ks * (double)(I - ks);
           if (ks > 0) {
-            double* F = ldlt_block(Lm, I, sm.sidx, ks, sm, cfg, Fg);
-            for (int p = tid; p < ks; p += DT) sm.xs[p] = sm.rhs[sm.sidx[sm.perm[p]]];
-            __syncthreads();
-            ldlt_solve(F, ks, sm.xs);
+            ldlt_block_solve(Lm, I, sm.sidx, ks, sm, cfg, Fg, [&]() { for (int p = tid; p < ks; p += DT) sm.xs[p] = sm.rhs[sm.sidx[sm.perm[p]]]; });
             for (int p = tid; p < ks; p += DT) sm.x[sm.sidx[sm.perm[p]]] = sm.xs[p];
           }
           for (int i = tid; i < I; i += DT)
@@ -1051,6 +1129,7 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
             for (int q = tid; q < nn; q += DT) { const int i = sm.perm[q]; sm.w[i] = sm.tmp[q] - sm.rhs[i]; }
             __syncthreads();
           }
+          TICK(T_W);
           // UpdatePreviousBestSolution (lcp.cc:127-137)
           int differs = 0;
           for (int i = tid; i < I; i += DT) differs |= (sm.x[i] != sm.bx[i]) || (sm.w[i] != sm.bw[i]);
@@ -1063,6 +1142,7 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
             }
             __syncthreads();
           }
+          TICK(T_BEST);
           ++iter;
         }
         pivots = iter;
@@ -1071,6 +1151,7 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
         if (!check_murty(Lm, I, sm, sm.x, sm.w, boxed, (iter >= max_it) ? 1e-8 : 0.0)) lcp_failed = 1;
       }
 
+      TICK(T_CHECK);
       // ---- 6. x_e = A_ee.ldlt().solve(b_e - A_ei x_i)  (lcp.cc:317) ----
       if (E > 0) {
         for (int i = tid; i < E; i += DT) {
@@ -1080,15 +1161,13 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
         }
         __syncthreads();
         work += (double)E * E * E / 3.0 + 2.0 * E * E + 2.0 * E * I;
-        double* F = ldlt_block(A, R, nullptr, E, sm, cfg, Fg);
-        for (int p = tid; p < E; p += DT) sm.xs[p] = sm.w[sm.perm[p]];
-        __syncthreads();
-        ldlt_solve(F, E, sm.xs);
+        ldlt_block_solve(A, R, nullptr, E, sm, cfg, Fg, [&]() { for (int p = tid; p < E; p += DT) sm.xs[p] = sm.w[sm.perm[p]]; });
         for (int p = tid; p < E; p += DT) lamv[sm.perm[p]] = sm.xs[p];
       }
       for (int i = tid; i < I; i += DT) lamv[E + i] = sm.x[i];
       __syncthreads();
 
+      TICK(T_XE);
       // ---- 7. outputs + a = M^-1 J^T lambda (per body, constraints in reference order) ----
       for (int i = tid; i < R; i += DT) {
         lam_out[i] = lamv[i];
@@ -1132,6 +1211,12 @@ __global__ void __launch_bounds__(DT, 2) egg_dense_kernel(EggDev d, double dt, d
     __syncthreads();
     integrate_world(d, w, dt, sm.sa);
     __syncthreads();
+#ifdef EGG_DENSE_TIMING
+    TICK(T_OUT);
+    if (tid < T_COUNT) atomicAdd(d.dbg + tid, s_prof[tid]);
+    if (tid == 0) atomicAdd(d.dbg + 31, 1ull);
+    __syncthreads();
+#endif
   }
 }
 
@@ -1216,10 +1301,7 @@ __global__ void __launch_bounds__(DT, 2) egg_relax_kernel(EggDev d, double dt, d
         for (int l = 0; l < 3; l++) A[(size_t)(3 * c + k) * R + 3 * c2 + l] = blk[3 * k + l];
     }
     __syncthreads();
-    double* F = ldlt_block(A, R, nullptr, R, sm, cfg, Fg);
-    for (int p = tid; p < R; p += DT) sm.xs[p] = e[sm.perm[p]];
-    __syncthreads();
-    ldlt_solve(F, R, sm.xs);
+    ldlt_block_solve(A, R, nullptr, R, sm, cfg, Fg, [&]() { for (int p = tid; p < R; p += DT) sm.xs[p] = e[sm.perm[p]]; });
     double* y = sm.w;
     for (int p = tid; p < R; p += DT) y[sm.perm[p]] = sm.xs[p];
     __syncthreads();

@@ -86,6 +86,7 @@ struct EggDev {
   unsigned* round_off;        // [groups][nrec+1] byte offset of every round inside the group stream
   int* grp_info;              // [groups][4] rounds, blocks in round 0, stream bytes
   int* work_ctr;              // [4] world-group queue of the persistent solve kernel
+  unsigned long long* dbg;    // [32] debug / phase-timing counters (written only by builds with EGG_DENSE_TIMING)
   int rec_fmt;                // 0: D diagonal in REC_DDIAG, multipliers in lam[]; 1: multipliers in REC_DDIAG, next-stage count in slot 29 (stream variant)
   EggParams prm;
 };

@@ -188,6 +188,10 @@ int egg_get_status(egg_batch* b, int* status, int* stats, double* residual);
  * Feeds the FP64 roofline of bench.py --workload c4. */
 int egg_get_dense_work(egg_batch* b, double* flops);
 
+/* Development aid: 32 device-side counters (phase cycle counts of the dense kernel when the
+ * library is built with EGG_DENSE_TIMING=1, zeros otherwise); reset != 0 clears them. */
+int egg_get_debug_counters(egg_batch* b, unsigned long long* out32, int reset);
+
 /* MPC rollout cost per world written to a DEVICE buffer of n_worlds doubles (feeds the NCCL
  * allgather): cost = -(x_body0 - x0_body0) + 10 (z_body0 - z0_body0)^2 with (x0,z0) the pose at
  * egg_init.  The reference has no cost function; this definition is ours. */

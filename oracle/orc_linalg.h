@@ -290,13 +290,17 @@ struct LDLT {
       }
       int rs = n - k - 1;
       if (k > 0) {
+        // The inner products run on fused multiply-adds: Eigen's product kernels are written with
+        // pmadd, which is an FMA on every -march=native x86-64 build with FMA3 (the reference's
+        // flags, common.mk:160,188), and an explicit std::fma pins the rounding independently of
+        // the compiler's contraction setting.
         for (int j = 0; j < k; j++) temp[j] = m(j, j) * m(k, j);
         double s = 0;
-        for (int j = 0; j < k; j++) s += m(k, j) * temp[j];
+        for (int j = 0; j < k; j++) s = std::fma(m(k, j), temp[j], s);
         m(k, k) -= s;
         for (int i = 0; i < rs; i++) {
           double t = 0;
-          for (int j = 0; j < k; j++) t += m(k + 1 + i, j) * temp[j];
+          for (int j = 0; j < k; j++) t = std::fma(m(k + 1 + i, j), temp[j], t);
           m(k + 1 + i, k) -= t;
         }
       }
@@ -315,7 +319,7 @@ struct LDLT {
     for (int k = 0; k < n; k++) if (tr[k] != k) std::swap(x[k], x[tr[k]]);
     for (int i = 0; i < n; i++) {           // L^-1
       double s = x[i];
-      for (int j = 0; j < i; j++) s -= m(i, j) * x[j];
+      for (int j = 0; j < i; j++) s = std::fma(-m(i, j), x[j], s);
       x[i] = s;
     }
     const double tol = 1.0 / std::numeric_limits<double>::max();
@@ -330,7 +334,7 @@ struct LDLT {
     // for bit.)
     for (int j = n - 1; j >= 1; j--) {
       const double xj = x[j];
-      for (int i = 0; i < j; i++) x[i] -= m(j, i) * xj;
+      for (int i = 0; i < j; i++) x[i] = std::fma(-m(j, i), xj, x[i]);
     }
     for (int k = n - 1; k >= 0; k--) if (tr[k] != k) std::swap(x[k], x[tr[k]]);
     return x;

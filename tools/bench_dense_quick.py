@@ -17,4 +17,9 @@ for s in range(steps):
     print(f"step {s}: narrow/assemble/solve ms = {ms[0]:.2f} {ms[1]:.2f} {ms[2]:.2f}  -> {W / (sum(ms[:3]) * 1e-3):.0f} world-steps/s; "
           f"pivots {st['pivots'].mean():.1f} rows {st['n_rows'].mean():.1f} status_or {int(np.bitwise_or.reduce(st['status']))} "
           f"flops/world {b.dense_work().mean():.3e}", flush=True)
+    c = b.debug_counters()
+    if c[31]:
+        names = ["rows+A", "cfm", "schur", "check", "index", "order", "gather", "factor", "solve", "w", "best", "x_e", "out", "f:A", "f:B", "f:C1", "f:C2", "s:fwd", "s:bwd"]
+        tot = float(c[:19].sum())
+        print("   phase cycles per world (timing build): " + ", ".join(f"{n} {c[i] / c[31]:.0f} ({100 * c[i] / tot:.1f}%)" for i, n in enumerate(names)), flush=True)
 b.close()
