@@ -17,7 +17,12 @@
 //
 // Dump format (little endian): char magic[8] = "EGGSTAT1"; int32 W, n, nj, solver, k_max, step;
 // double dt; then m[W n], I[W n 9], joints i0[W nj], i1[W nj] (int32), c0[W nj 3], c1[W nj 3],
-// p[W n 3], R[W n 9], v[W n 3], w[W n 3] (doubles, world-major as in include/egg_cuda.h).
+// f_ext[W n 6], p[W n 3], R[W n 9], v[W n 3], w[W n 3] (doubles, world-major as in
+// include/egg_cuda.h).  f_ext is part of the state: the reference freezes M^-1 and the external
+// force / gyroscopic torque at Init (ensembles.cc:202-222 are never refreshed by Step), so a replay
+// that re-initialised from the dumped velocities would see a different torque.  (M^-1 is
+// recomputed by egg_init from the dumped R: identical for bodies with isotropic inertia, which is
+// every body of the reference's scenes.)
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -38,7 +43,7 @@ namespace {
 struct Dump {
   int32_t W = 0, n = 0, nj = 0, solver = 1, k_max = 500, step = 0;
   double dt = 0.001;
-  std::vector<double> m, I, c0, c1, p, R, v, w;
+  std::vector<double> m, I, c0, c1, fext, p, R, v, w;
   std::vector<int32_t> i0, i1;
 };
 
@@ -63,7 +68,7 @@ void save(const Dump& d, const char* path) {
   const int32_t hdr[6] = {d.W, d.n, d.nj, d.solver, d.k_max, d.step};
   std::fwrite(hdr, sizeof(int32_t), 6, f);
   std::fwrite(&d.dt, sizeof(double), 1, f);
-  put(f, d.m); put(f, d.I); put(f, d.i0); put(f, d.i1); put(f, d.c0); put(f, d.c1);
+  put(f, d.m); put(f, d.I); put(f, d.i0); put(f, d.i1); put(f, d.c0); put(f, d.c1); put(f, d.fext);
   put(f, d.p); put(f, d.R); put(f, d.v); put(f, d.w);
   std::fclose(f);
 }
@@ -78,7 +83,7 @@ Dump load(const char* path) {
   if (std::fread(hdr, sizeof(int32_t), 6, f) != 6 || std::fread(&d.dt, sizeof(double), 1, f) != 1) Panic("short read");
   d.W = hdr[0]; d.n = hdr[1]; d.nj = hdr[2]; d.solver = hdr[3]; d.k_max = hdr[4]; d.step = hdr[5];
   const size_t W = d.W, n = d.n, nj = d.nj;
-  get(f, d.m, W * n); get(f, d.I, W * n * 9); get(f, d.i0, W * nj); get(f, d.i1, W * nj); get(f, d.c0, W * nj * 3); get(f, d.c1, W * nj * 3);
+  get(f, d.m, W * n); get(f, d.I, W * n * 9); get(f, d.i0, W * nj); get(f, d.i1, W * nj); get(f, d.c0, W * nj * 3); get(f, d.c1, W * nj * 3); get(f, d.fext, W * n * 6);
   get(f, d.p, W * n * 3); get(f, d.R, W * n * 9); get(f, d.v, W * n * 3); get(f, d.w, W * n * 3);
   std::fclose(f);
   return d;
@@ -94,6 +99,7 @@ egg_batch* make_batch(const Dump& d) {
   check(egg_set_bodies(b, d.p.data(), d.R.data(), d.v.data(), d.w.data(), d.m.data(), d.I.data(), nullptr), "egg_set_bodies");
   if (d.nj) check(egg_set_joints(b, d.i0.data(), d.i1.data(), d.c0.data(), d.c1.data()), "egg_set_joints");
   check(egg_init(b), "egg_init");
+  if (!d.fext.empty()) check(egg_set_external(b, d.fext.data()), "egg_set_external");   // a replay: the torque frozen at the original Init
   return b;
 }
 
@@ -168,6 +174,8 @@ int main(int argc, char** argv) {
     check(egg_step(b, d.dt, EGG_OPEN_DYNAMICS_ENGINE, steps), "egg_step");
     fetch(b, d);
     d.step = steps;
+    d.fext.resize((size_t)W * links * 6);
+    check(egg_get_static(b, nullptr, nullptr, d.fext.data()), "egg_get_static");
     save(d, argv[5]);
     check(egg_step(b, d.dt, EGG_OPEN_DYNAMICS_ENGINE, steps), "egg_step");
     fetch(b, d);

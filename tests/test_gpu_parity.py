@@ -73,7 +73,14 @@ def test_pgs_fixed_k20_stepwise(name, W, steps):
 def test_cairn_pgs_falling():
     import eggshell_b200 as E
     scene = E.scenes.cairn(16, rocks=4, zb=(0.2, 1.0), seed=11)
-    worst = _stepwise(scene, 30, list(range(16)), dict(solver=E.SOLVER_PGS), dict(solver=1))
+    # Multipliers at 1e-8 here (1e-9 everywhere else): the rocks land on several vertices, so the
+    # contact rows of a rock are redundant (6 DOF) and lambda is fixed only by the cfm = 0.01
+    # regularisation.  The solve stops at a residual of 1e-9 (constants.h:5), which leaves lambda
+    # free within residual x 1/cfm: two arithmetic paths that both satisfy the reference's stopping
+    # test differ by up to ~1e-7 absolute on |lambda| ~ 1e3 (tools/diag_cairn_lam.py), while the
+    # quantities that do not depend on the split between redundant rows -- v, w, p, R -- agree to
+    # 1e-13.
+    worst = _stepwise(scene, 30, list(range(16)), dict(solver=E.SOLVER_PGS), dict(solver=1), lam_tol=1e-8)
     print("cairn worst", worst)
 
 
