@@ -96,6 +96,62 @@ __device__ bool sat_test(const BoxD& b1, const BoxD& b2, Sat& s) {
   return true;
 }
 
+// The same 15 axis tests when only the verdict "collide or not" is wanted (phase 1: collision.cc:218,249
+// return false on the first positive separation): no normalisation, no tracking of the deepest
+// axis.  An edge axis is skipped when its length is <= 1e-9 (collision.cc:240): the length is only
+// compared with the threshold, so the square root is taken only when the squared length is
+// within a hair of 1e-18 (the comparison on the root is then evaluated exactly as in sat_test).
+__device__ bool sat_hits(const BoxD& b1, const BoxD& b2) {
+  const double kTolerance = 1e-9;
+  const double* R1 = b1.R;
+  const double* R2 = b2.R;
+  double R[9], Q[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[3 * i + j] = R1[i] * R2[j] + R1[3 + i] * R2[3 + j] + R1[6 + i] * R2[6 + j];
+  const d3 p = mtmulv(R1, b2.c - b1.c);
+  for (int k = 0; k < 9; k++) Q[k] = fabs(R[k]);
+  const d3 H1 = b1.h, H2 = b2.h;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double separation = fabs(get3(p, i)) - (get3(H1, i) + dot3(H2, mrow(Q, i)));
+    if (separation > 0) return false;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const double e1 = dot3(mcol(R, i), p);
+    const double separation = fabs(e1) - (dot3(H1, mcol(Q, i)) + get3(H2, i));
+    if (separation > 0) return false;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+    const int ia = (i == 0) ? 1 : 0, ib = (i == 2) ? 1 : 2;
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      const int ja = (j == 0) ? 1 : 0, jb = (j == 2) ? 1 : 2;
+      d3 nn = mk3(0, 0, 0);
+      set3(nn, i1, -R[3 * i2 + j]);
+      set3(nn, i2, R[3 * i1 + j]);
+      const double l2 = dot3(nn, nn);
+      if (l2 < 0.99e-18) continue;                               // len <= 1e-9 for certain
+      if (l2 < 1.01e-18 && !(sqrt(l2) > kTolerance)) continue;   // borderline: the reference's own test
+      const double e1 = get3(p, i2) * R[3 * i1 + j] - get3(p, i1) * R[3 * i2 + j];
+      const double extent = get3(H1, ia) * Q[3 * ib + j] + get3(H1, ib) * Q[3 * ia + j] +
+                            get3(H2, ja) * Q[3 * i + jb] + get3(H2, jb) * Q[3 * i + ja];
+      if (fabs(e1) - extent > 0) return false;
+    }
+  }
+  return true;
+}
+
+// norm3(v) < dmin without the square root unless |v|^2 is within a hair of dmin^2.
+__device__ __forceinline__ bool closer_than(d3 v, double dmin) {
+  const double d2 = dot3(v, v), t2 = dmin * dmin;
+  if (d2 > t2 * 1.000001) return false;
+  if (d2 < t2 * 0.999999) return dmin > 0;
+  return sqrt(d2) < dmin;
+}
+
 // collision.cc:47-62
 __device__ void line_closest_approach(d3 pa, d3 ua, d3 pb, d3 ub, double* alpha, double* beta) {
   d3 p = pb - pa;
@@ -269,7 +325,8 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
   double* sp = sm;                 // [3][n]
   double* sR = sm + 3 * n;         // [9][n]
   double* sside = sm + 12 * n;     // [3][n]
-  unsigned short* hitlist = (unsigned short*)(sm + 15 * n);          // [P]
+  double* srad = sm + 15 * n;      // [n] bounding-sphere radius |h|
+  unsigned short* hitlist = (unsigned short*)(sm + 16 * n);          // [P] cull survivors, then colliding pairs
   unsigned char* hit = (unsigned char*)(hitlist + ((P + 3) & ~3));   // [P]
   __shared__ int wsum[NT / 32];
   __shared__ int s_flags;
@@ -280,6 +337,7 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
   for (int i = tid; i < 3 * n; i += NT) sside[i] = bpar[i];
   if (tid == 0) s_flags = 0;
   __syncthreads();
+  for (int b = tid; b < n; b += NT) srad[b] = norm3(mk3(sside[b] * 0.5, sside[n + b] * 0.5, sside[2 * n + b] * 0.5));
 
   int* c_i0 = d.c_i0 + (size_t)w * d.maxc;
   int* c_i1 = d.c_i1 + (size_t)w * d.maxc;
@@ -326,25 +384,45 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
   }
   raw = base;
 
-  // ---- phase 1: SAT over all pairs, hit flags ----
-  for (int q = tid; q < P; q += NT) {
+  // ---- phase 1: cull, then SAT on the survivors; hit flags ----
+  // Conservative cull in front of the SAT (the reference's own broadphase,
+  // toolkit/collision.cc:58-109, is unused by Ensemble::UpdateContacts): boxes whose bounding
+  // spheres are apart by a 1e-3 relative margin are disjoint, so one of the 15 axes separates
+  // them by a margin far above rounding and CollideBoxes returns false (collision.cc:218,249).
+  // The colliding-pair list is unchanged (tests/test_gpu_parity.py::test_broadphase_cull_keeps_pair_list);
+  // EGG_OPT_NO_BROADPHASE_CULL (quirks bit 8) runs the SAT on every pair.  The survivors are
+  // compacted first (order irrelevant here) so that the SAT runs on full warps.
+  __syncthreads();                 // srad
+  int nsurv = 0;
+  {
+    const bool nocull = (d.prm.quirks & 8) != 0;
+    for (int q0 = 0; q0 < P; q0 += NT) {
+      const int q = q0 + tid;
+      int keep = 0;
+      if (q < P) {
+        int i, j;
+        pair_from_index(q, n, &i, &j);
+        const d3 dc = mk3(sp[j] - sp[i], sp[n + j] - sp[n + i], sp[2 * n + j] - sp[2 * n + i]);
+        const double rr = srad[i] + srad[j];
+        keep = (nocull || !(dot3(dc, dc) > rr * rr * 1.002)) ? 1 : 0;
+        hit[q] = 0;
+        if (d.pair_code) { d.pair_code[(size_t)w * P + q] = 0; d.pair_cnt[(size_t)w * P + q] = 0; }
+      }
+      int tot;
+      const int off = block_excl_scan<NT>(keep, &tot, wsum);
+      if (keep) hitlist[nsurv + off] = (unsigned short)q;
+      nsurv += tot;
+    }
+  }
+  __syncthreads();
+  for (int h = tid; h < nsurv; h += NT) {
+    const int q = hitlist[h];
     int i, j;
     pair_from_index(q, n, &i, &j);
     BoxD b1, b2;
     load_box(sp, sR, sside, n, i, b1);
     load_box(sp, sR, sside, n, j, b2);
-    Sat s;
-    // Conservative cull in front of the SAT (the reference's own broadphase,
-    // toolkit/collision.cc:58-109, is unused by Ensemble::UpdateContacts): boxes whose bounding
-    // spheres are apart by a 1e-3 relative margin are disjoint, so one of the 15 axes separates
-    // them by a margin far above rounding and CollideBoxes returns false (collision.cc:218,249).
-    // The colliding-pair list is unchanged (tests/test_gpu_parity.py::test_broadphase_cull_keeps_pair_list);
-    // EGG_OPT_NO_BROADPHASE_CULL (quirks bit 8) runs the SAT on every pair.
-    const d3 dc = b2.c - b1.c;
-    const double rr = norm3(b1.h) + norm3(b2.h);
-    const bool apart = !(d.prm.quirks & 8) && dot3(dc, dc) > rr * rr * 1.002;
-    hit[q] = (!apart && sat_test(b1, b2, s)) ? 1 : 0;
-    if (d.pair_code) { d.pair_code[(size_t)w * P + q] = 0; d.pair_cnt[(size_t)w * P + q] = 0; }
+    if (sat_hits(b1, b2)) hit[q] = 1;
   }
   __syncthreads();
 
@@ -395,14 +473,14 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
         d3 jp = (p0 + p1) / 2.0;
         for (int c = 0; c < rawcnt; c++) {
           d3 cp = mk3(cb[7 * c], cb[7 * c + 1], cb[7 * c + 2]);
-          if (norm3(jp - cp) < dmin) del |= 1u << c;
+          if (closer_than(jp - cp, dmin)) del |= 1u << c;
         }
       }
       for (int a = 0; a < rawcnt; a++)
         for (int b = a + 1; b < rawcnt; b++) {
           d3 pa = mk3(cb[7 * a], cb[7 * a + 1], cb[7 * a + 2]);
           d3 pb = mk3(cb[7 * b], cb[7 * b + 1], cb[7 * b + 2]);
-          if (norm3(pa - pb) < dmin) del |= 1u << b;
+          if (closer_than(pa - pb, dmin)) del |= 1u << b;
         }
       for (int c = 0; c < rawcnt; c++)
         if (!(del & (1u << c))) {
@@ -465,7 +543,7 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
 
 }  // namespace
 
-size_t egg_collide_smem(const EggDev& d) { return (size_t)15 * d.n * sizeof(double) + (size_t)((d.P + 3) & ~3) * 2 + (size_t)((d.P + 7) & ~7); }
+size_t egg_collide_smem(const EggDev& d) { return (size_t)16 * d.n * sizeof(double) + (size_t)((d.P + 3) & ~3) * 2 + (size_t)((d.P + 7) & ~7); }
 
 cudaError_t egg_launch_collide(const EggDev& d, cudaStream_t s) {
   const size_t smem = egg_collide_smem(d);

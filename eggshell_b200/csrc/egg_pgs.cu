@@ -32,7 +32,8 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
   const int n = d.n, nj = d.nj, w = blockIdx.x, tid = threadIdx.x;
   double* sdyn = sm;                         // [18][n]
   double* sst = sm + EGG_DYN * n;            // [16][n]
-  int* si0 = (int*)(sm + (EGG_DYN + EGG_STAT) * n);   // [nrec]
+  double* su = sm + (EGG_DYN + EGG_STAT) * n;         // [6][n] u = v/dt + M^-1 f per body
+  int* si0 = (int*)(su + 6 * n);                       // [nrec]
   int* si1 = si0 + d.nrec;                   // [nrec]
   int* slot = si1 + d.nrec;                  // [nrec] record slot of c
   int* lev = slot + d.nrec;                  // [nrec] dependency level of c
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
   for (int b = tid; b < n; b += NT) blast[b] = -1;
   for (int c = tid; c <= nc; c += NT) lstart[c] = 0;
   __syncthreads();
+  egg_body_u(n, sdyn, sst, dt, su, tid, NT);
 
   int* gstage = d.level_start ? d.level_start + (size_t)w * (d.nrec + 1) : nullptr;
   if (tid == 0) {
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(NT) egg_assemble_kernel(EggDev d, double dt, i
   for (int c = tid; c < nc; c += NT) {
     const int i0 = si0[c], i1 = si1[c];
     double v[EGG_REC];
-    egg_build_record(d, w, c, i0, i1, sdyn, sst, geom, dt, false, v);
+    egg_build_record(d, w, c, i0, i1, sdyn, sst, su, geom, dt, false, v);
     if (d.slot_of) d.slot_of[(size_t)w * d.nrec + c] = slot[c];
     double2* out = reinterpret_cast<double2*>(recw + (size_t)slot[c] * EGG_REC);
 #pragma unroll
@@ -137,7 +139,7 @@ int egg_stage_cap(const EggDev& d) {
 }
 
 size_t egg_assemble_smem(const EggDev& d) {
-  return (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double) + (size_t)(7 * d.nrec + d.n + 8) * sizeof(int);
+  return (size_t)(EGG_DYN + EGG_STAT + 6) * d.n * sizeof(double) + (size_t)(7 * d.nrec + d.n + 8) * sizeof(int);
 }
 
 cudaError_t egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s) {

@@ -267,15 +267,18 @@ __global__ void __launch_bounds__(128) egg_rounds_kernel(EggDev d, int G) {
 
 // Assembly 3/3: one CTA per world builds the records and writes them at their round positions.
 template <int NT>
-__global__ void __launch_bounds__(NT) egg_records_kernel(EggDev d, double dt, int G) {
+__global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : 4) egg_records_kernel(EggDev d, double dt, int G) {
   extern __shared__ double sm[];
   const int n = d.n, nj = d.nj, w = blockIdx.x, tid = threadIdx.x, nrec = d.nrec;
   double* sdyn = sm;                         // [18][n]
   double* sst = sm + EGG_DYN * n;            // [16][n]
+  double* su = sst + EGG_STAT * n;           // [6][n] u = v/dt + M^-1 f per body
   const double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
   const double* st = d.stat + (size_t)w * EGG_STAT * n;
   for (int i = tid; i < EGG_DYN * n; i += NT) sdyn[i] = dyn[i];
   for (int i = tid; i < EGG_STAT * n; i += NT) sst[i] = st[i];
+  __syncthreads();
+  egg_body_u(n, sdyn, sst, dt, su, tid, NT);
   __syncthreads();
   const int nc = nj + d.c_count[w];
   const int g = w / G, sub = w % G;
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(NT) egg_records_kernel(EggDev d, double dt, in
     if (c < nj) { i0 = d.j_i0[(size_t)w * nj + c]; i1 = d.j_i1[(size_t)w * nj + c]; }
     else { i0 = c_i0[c - nj]; i1 = c_i1[c - nj]; }
     double v[EGG_REC];
-    egg_build_record(d, w, c, i0, i1, sdyn, sst, geom, dt, true, v);
+    egg_build_record(d, w, c, i0, i1, sdyn, sst, su, geom, dt, true, v);
     const int p = cp[c], stg = p >> 8, idx = p & 255;
     const unsigned ro = roff[stg];
     const unsigned start = gs[ro + sub];
@@ -818,7 +821,7 @@ size_t egg_stream_rec_bytes(int W, int nrec, int lpw) {
 
 size_t egg_stream_smem(const EggDev& d) {
   const size_t solve = (d.blkb == RECB32 + LAMB) ? stream_smem<true>(d, d.lpw) : stream_smem<false>(d, d.lpw);
-  const size_t recs = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double);
+  const size_t recs = (size_t)(EGG_DYN + EGG_STAT + 6) * d.n * sizeof(double);
   const size_t sched = schedule_per_world(d);
   size_t m = solve > recs ? solve : recs;
   return m > sched ? m : sched;
@@ -840,7 +843,7 @@ cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t 
   }
   const int ngroups = (d.W + G - 1) / G;
   egg_rounds_kernel<<<(ngroups + 3) / 4, 128, 0, s>>>(d, G);
-  const size_t smem = (size_t)(EGG_DYN + EGG_STAT) * d.n * sizeof(double);
+  const size_t smem = (size_t)(EGG_DYN + EGG_STAT + 6) * d.n * sizeof(double);
   if (d.nrec <= 128) {
     if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (e != cudaSuccess) return e;

@@ -42,10 +42,29 @@ __device__ inline void egg_align_to_z(d3 nrm, double* R) {
   R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
 }
 
+// u = v/dt + M^-1 f per body (the vector the rhs multiplies J with, ensembles.cc:569-570), computed
+// once per body as the reference does (not once per constraint side): su [6][n] from the world's
+// dyn [18][n] and stat [16][n].  Call with all threads of the CTA, then synchronise.
+__device__ inline void egg_body_u(int n, const double* sdyn, const double* sst, double dt, double* su, int tid, int nthreads) {
+  for (int b = tid; b < n; b += nthreads) {
+    const double mi = sst[b];
+    double Ii[9];
+    for (int k = 0; k < 9; k++) Ii[k] = sst[(1 + k) * n + b];
+    d3 v = mk3(sdyn[12 * n + b], sdyn[13 * n + b], sdyn[14 * n + b]);
+    d3 wv = mk3(sdyn[15 * n + b], sdyn[16 * n + b], sdyn[17 * n + b]);
+    d3 fl = mk3(sst[10 * n + b], sst[11 * n + b], sst[12 * n + b]);
+    d3 ft = mk3(sst[13 * n + b], sst[14 * n + b], sst[15 * n + b]);
+    d3 ul = v / dt + fl * mi;
+    d3 ua = wv / dt + mmulv(Ii, ft);
+    su[b] = ul.x; su[n + b] = ul.y; su[2 * n + b] = ul.z;
+    su[3 * n + b] = ua.x; su[4 * n + b] = ua.y; su[5 * n + b] = ua.z;
+  }
+}
+
 // Record of constraint c (joints first, then contacts) of world w whose bodies are (i0, i1).
-// sdyn / sst = the world's dyn [18][n] and stat [16][n] arrays (shared memory or global).
-// lam_in_rec: REC_DDIAG holds the multipliers (x0 = rhs) instead of the D diagonal.
-__device__ inline void egg_build_record(const EggDev& d, int w, int c, int i0, int i1, const double* sdyn, const double* sst,
+// sdyn / sst = the world's dyn [18][n] and stat [16][n] arrays, su = egg_body_u's [6][n] (shared
+// memory or global).  lam_in_rec: REC_DDIAG holds the multipliers (x0 = rhs) instead of the D diagonal.
+__device__ inline void egg_build_record(const EggDev& d, int w, int c, int i0, int i1, const double* sdyn, const double* sst, const double* su,
                                         const double* geom, double dt, bool lam_in_rec, double* v) {
   const int n = d.n, nj = d.nj, maxc = d.maxc;
   const double erp = d.prm.erp, cfm = d.prm.cfm;
@@ -105,12 +124,8 @@ __device__ inline void egg_build_record(const EggDev& d, int w, int c, int i0, i
     double Ii[9];
     for (int k = 0; k < 9; k++) Ii[k] = sst[(1 + k) * n + b];
     const double sg = side ? 1.0 : -1.0;
-    d3 v = mk3(sdyn[12 * n + b], sdyn[13 * n + b], sdyn[14 * n + b]);
-    d3 wv = mk3(sdyn[15 * n + b], sdyn[16 * n + b], sdyn[17 * n + b]);
-    d3 fl = mk3(sst[10 * n + b], sst[11 * n + b], sst[12 * n + b]);
-    d3 ft = mk3(sst[13 * n + b], sst[14 * n + b], sst[15 * n + b]);
-    d3 ul = v / dt + fl * mi;
-    d3 ua = wv / dt + mmulv(Ii, ft);
+    d3 ul = mk3(su[b], su[n + b], su[2 * n + b]);
+    d3 ua = mk3(su[3 * n + b], su[4 * n + b], su[5 * n + b]);
     for (int k = 0; k < 3; k++) {
       d3 lin = jl[k] * sg;
       d3 ang = side ? ja1[k] : ja0[k];
@@ -127,9 +142,10 @@ __device__ inline void egg_build_record(const EggDev& d, int w, int c, int i0, i
   v[REC_R0] = r0.x; v[REC_R0 + 1] = r0.y; v[REC_R0 + 2] = r0.z;
   v[REC_R1] = r1.x; v[REC_R1 + 1] = r1.y; v[REC_R1 + 2] = r1.z;
   v[REC_DOFF] = D[3]; v[REC_DOFF + 1] = D[6]; v[REC_DOFF + 2] = D[7];
+  const double erp_dt2 = -erp / dt / dt;      // ensembles.cc:569
   for (int k = 0; k < 3; k++) {
     v[REC_INVA + k] = 1.0 / (D[4 * k] + cfm);
-    v[REC_RHS + k] = -erp / dt / dt * get3(err, k) - Ju[k];
+    v[REC_RHS + k] = erp_dt2 * get3(err, k) - Ju[k];
     v[REC_DDIAG + k] = lam_in_rec ? v[REC_RHS + k] : D[4 * k];
   }
   v[REC_IDX] = __hiloint2double(i1, i0);
