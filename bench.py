@@ -343,6 +343,30 @@ def run_ours(args):
                    "kernel_ms_per_step": {"narrowphase": k3[0] / max(k3[3], 1.0), "assembly": k3[1] / max(k3[3], 1.0), "solve_integrate": k3[2] / max(k3[3], 1.0)},
                    "status_or": int(np.bitwise_or.reduce(st3["status"])), "parity": "tests/test_gpu_parity.py::test_pgs_fixed_k20_stepwise"}
 
+    # ---- strong-scaling extra (BASELINE.json configs[2] read as "65536 worlds on 1/2/4/8 GPUs"): the
+    # workload's single-GPU world count split over the ranks, same step, device-timed max over ranks ----
+    strong = None
+    if world > 1 and args.workload == "c3" and not args.no_fixed_k:
+        Ws = max(1, Wd // world)
+        b.close()
+        sub = scene_for(args, Ws, rank)
+        b = E.scenes.make_batch(sub, solver=E.SOLVER_PGS, k_max=args.k_max, max_contacts=maxc, device=local, precision=args.precision)
+        b.set_stream(stream.cuda_stream)
+        b.snapshot()
+        for _ in range(2):
+            b.restore(); b.step(dt)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        for _ in range(args.steps):
+            b.restore(); b.step(dt)
+        h1.record(stream)
+        barrier()
+        t4 = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        strong = {"worlds_total": Ws * world, "worlds_per_gpu": Ws, "value": Ws * world * args.steps / (float(t4.item()) * 1e-3), "unit": "world-steps/s",
+                  "ms_per_step": float(t4.item()) / max(args.steps, 1), "k_max": args.k_max}
+
     if rank == 0:
         pk, pk_kind = peaks()
         steps_counted = max(kms[3], 1.0)
@@ -429,6 +453,8 @@ def run_ours(args):
         }
         if fixed_k is not None:
             line["fixed_k"] = fixed_k
+        if strong is not None:
+            line["strong_scaling"] = strong
         emit(line)
     b.close()
     if world > 1:

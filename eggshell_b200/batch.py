@@ -21,7 +21,7 @@ EXPLICIT_EULER, OPEN_DYNAMICS_ENGINE, IMPLICIT_MIDPOINT = 0, 1, 2
 ST_LCP_FAILED, ST_JOINT_CONFLICT, ST_BAD_INIT, ST_CONTACT_OVERFLOW, ST_NONFINITE = 1, 2, 4, 8, 16
 
 EXPORTS = [
-    "egg_desc_default", "egg_create", "egg_destroy", "egg_set_bodies", "egg_set_state", "egg_set_joints",
+    "egg_desc_default", "egg_create", "egg_destroy", "egg_set_bodies", "egg_set_shapes", "egg_set_state", "egg_set_joints",
     "egg_set_external", "egg_init", "egg_init_stabilize", "egg_post_stabilize", "egg_step", "egg_snapshot", "egg_restore", "egg_update_contacts", "egg_get_static", "egg_get_bodies", "egg_get_contacts", "egg_get_contacts_range", "egg_get_pair_hits", "egg_get_pair_hits_range",
     "egg_get_status", "egg_get_dense_work", "egg_get_debug_counters", "egg_rollout_costs", "egg_set_stream", "egg_sync", "egg_device_bytes",
     "egg_launch_count", "egg_capacity", "egg_set_profiling", "egg_get_kernel_ms", "egg_fp64_peak_tflops", "egg_host_alloc", "egg_host_free", "egg_last_error", "egg_version",
@@ -139,6 +139,12 @@ class Batch:
         m = _d(m, (W, n))
         s = None if side is None else _d(side, (W, n, 3))
         _chk(lib().egg_set_bodies(self.h, _p(p), _p(R), _p(v), _p(w), _p(m), _p(I), _p(s)), "egg_set_bodies")
+
+    def set_shapes(self, shape, dims):
+        """Colliders: 0 box (dims = side lengths), 1 sphere (radius), 2 capsule (radius, axis length)."""
+        W, n = self.W, self.n
+        shape = np.ascontiguousarray(np.broadcast_to(np.asarray(shape, dtype=np.int32), (W, n)))
+        _chk(lib().egg_set_shapes(self.h, _p(shape), _p(_d(dims, (W, n, 3)))), "egg_set_shapes")
 
     def set_state(self, p=None, R=None, v=None, w=None):
         W, n = self.W, self.n

@@ -375,6 +375,21 @@ int egg_set_bodies(egg_batch* b, const double* p, const double* R, const double*
   return EGG_OK;
 }
 
+int egg_set_shapes(egg_batch* b, const int* shape, const double* dims) {
+  if (!b || !shape || !dims) return EGG_ERR_ARG;
+  CK(cudaSetDevice(b->device));
+  const size_t cnt = (size_t)b->dev.W * b->dev.n;
+  std::vector<double> t(cnt);
+  for (size_t k = 0; k < cnt; k++) {
+    if (shape[k] < 0 || shape[k] > 2) { g_err = "collider shape must be 0 (box), 1 (sphere) or 2 (capsule)"; return EGG_ERR_ARG; }
+    t[k] = (double)shape[k];
+  }
+  RET(upload(b, t.data(), b->dev.n, 1, b->dev.bpar, EGG_BPAR, 13));
+  CK(cudaStreamSynchronize(b->stream));      // t is a temporary
+  RET(upload(b, dims, b->dev.n, 3, b->dev.bpar, EGG_BPAR, 0));
+  return EGG_OK;
+}
+
 int egg_set_joints(egg_batch* b, const int* i0, const int* i1, const double* c0, const double* c1) {
   if (!b) return EGG_ERR_ARG;
   const int nj = b->dev.nj;

@@ -325,8 +325,9 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
   double* sp = sm;                 // [3][n]
   double* sR = sm + 3 * n;         // [9][n]
   double* sside = sm + 12 * n;     // [3][n]
-  double* srad = sm + 15 * n;      // [n] bounding-sphere radius |h|
-  unsigned short* hitlist = (unsigned short*)(sm + 16 * n);          // [P] cull survivors, then colliding pairs
+  double* srad = sm + 15 * n;      // [n] bounding-sphere radius
+  double* sshape = sm + 16 * n;    // [n] collider: 0 box, 1 sphere, 2 capsule (sside = its dims)
+  unsigned short* hitlist = (unsigned short*)(sm + 17 * n);          // [P] cull survivors, then colliding pairs
   unsigned char* hit = (unsigned char*)(hitlist + ((P + 3) & ~3));   // [P]
   __shared__ int wsum[NT / 32];
   __shared__ int s_flags;
@@ -335,9 +336,14 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
   const double* bpar = d.bpar + (size_t)w * EGG_BPAR * n;
   for (int i = tid; i < 12 * n; i += NT) sm[i] = dyn[i];
   for (int i = tid; i < 3 * n; i += NT) sside[i] = bpar[i];
+  for (int i = tid; i < n; i += NT) sshape[i] = bpar[13 * n + i];
   if (tid == 0) s_flags = 0;
   __syncthreads();
-  for (int b = tid; b < n; b += NT) srad[b] = norm3(mk3(sside[b] * 0.5, sside[n + b] * 0.5, sside[2 * n + b] * 0.5));
+  for (int b = tid; b < n; b += NT) {
+    const int shp = (int)sshape[b];
+    srad[b] = (shp == 0) ? norm3(mk3(sside[b] * 0.5, sside[n + b] * 0.5, sside[2 * n + b] * 0.5))
+                         : (shp == 1 ? sside[b] : sside[n + b] * 0.5 + sside[b]);
+  }
 
   int* c_i0 = d.c_i0 + (size_t)w * d.maxc;
   int* c_i1 = d.c_i1 + (size_t)w * d.maxc;
@@ -357,15 +363,29 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
       d3 c1 = mk3(sR[1 * n + b], sR[4 * n + b], sR[7 * n + b]);
       d3 c2 = mk3(sR[2 * n + b], sR[5 * n + b], sR[8 * n + b]);
       double s0 = sside[b], s1 = sside[n + b], s2 = sside[2 * n + b];
-      int k = 0;
-      for (int x = -1; x <= 1; x += 2)
-        for (int y = -1; y <= 1; y += 2)
-          for (int z = -1; z <= 1; z += 2) {
-            d3 v = c + c0 * s0 * 0.5 * (double)x + c1 * s1 * 0.5 * (double)y + c2 * s2 * 0.5 * (double)z;
-            vert[k] = v;
-            if (v.z < 0) mask |= 1u << k;
-            k++;
-          }
+      const int shp = (int)sshape[b];
+      if (shp == 0) {
+        int k = 0;
+        for (int x = -1; x <= 1; x += 2)
+          for (int y = -1; y <= 1; y += 2)
+            for (int z = -1; z <= 1; z += 2) {
+              d3 v = c + c0 * s0 * 0.5 * (double)x + c1 * s1 * 0.5 * (double)y + c2 * s2 * 0.5 * (double)z;
+              vert[k] = v;
+              if (v.z < 0) mask |= 1u << k;
+              k++;
+            }
+      } else {
+        // sphere / capsule (oracle/orc_collision.h collide_round_and_ground): the lowest point of each
+        // end sphere, -z end first; s0 = radius, s1 = axis length
+        const int ends = (shp == 2) ? 2 : 1;
+        for (int e = 0; e < ends; e++) {
+          d3 ce = c;
+          if (shp == 2) ce = c + c2 * (s1 * 0.5 * (e == 0 ? -1.0 : 1.0));
+          d3 v = mk3(ce.x, ce.y, ce.z - s0);
+          vert[e] = v;
+          if (v.z < 0) mask |= 1u << e;
+        }
+      }
     }
     int cnt = __popc(mask), tot;
     int off = block_excl_scan<NT>(cnt, &tot, wsum);
@@ -419,10 +439,17 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
     const int q = hitlist[h];
     int i, j;
     pair_from_index(q, n, &i, &j);
-    BoxD b1, b2;
-    load_box(sp, sR, sside, n, i, b1);
-    load_box(sp, sR, sside, n, j, b2);
-    if (sat_hits(b1, b2)) hit[q] = 1;
+    const int s1 = (int)sshape[i], s2 = (int)sshape[j];
+    if (s1 == 0 && s2 == 0) {
+      BoxD b1, b2;
+      load_box(sp, sR, sside, n, i, b1);
+      load_box(sp, sR, sside, n, j, b2);
+      if (sat_hits(b1, b2)) hit[q] = 1;
+    } else if (s1 == 1 && s2 == 1) {          // sphere - sphere (oracle/orc_collision.h collide_spheres)
+      const d3 dc = mk3(sp[j] - sp[i], sp[n + j] - sp[n + i], sp[2 * n + j] - sp[2 * n + i]);
+      const double depth = (sside[i] + sside[j]) - norm3(dc);
+      if (depth > 0) hit[q] = 1;
+    }                                          // other collider pairs: no pairwise narrowphase
   }
   __syncthreads();
 
@@ -453,9 +480,20 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
       BoxD b1, b2;
       load_box(sp, sR, sside, n, bi, b1);
       load_box(sp, sR, sside, n, bj, b2);
-      Sat s;
-      sat_test(b1, b2, s);
-      rawcnt = manifold(b1, b2, s, &code, cb);
+      if ((int)sshape[bi] == 1) {               // sphere - sphere: one contact in the middle of the overlap
+        const d3 dc = b2.c - b1.c;
+        const double dist = norm3(dc), r1 = sside[bi], r2 = sside[bj];
+        const double depth = (r1 + r2) - dist;
+        const d3 nn = (dist > 0) ? dc / dist : mk3(0, 0, 1);
+        const d3 pos = b1.c + nn * (r1 - depth * 0.5);
+        cb[0] = pos.x; cb[1] = pos.y; cb[2] = pos.z; cb[3] = nn.x; cb[4] = nn.y; cb[5] = nn.z; cb[6] = depth;
+        code = 17;
+        rawcnt = 1;
+      } else {
+        Sat s;
+        sat_test(b1, b2, s);
+        rawcnt = manifold(b1, b2, s, &code, cb);
+      }
       if (d.pair_code) { d.pair_code[(size_t)w * P + q] = (unsigned char)code; d.pair_cnt[(size_t)w * P + q] = (unsigned char)rawcnt; }
       // CheckAndCorrectEnsembleState, restricted to this body pair (ensembles.cc:264-313):
       // joint-contact closer than dmin => drop the contact; contact-contact => drop the later.
@@ -543,7 +581,7 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
 
 }  // namespace
 
-size_t egg_collide_smem(const EggDev& d) { return (size_t)16 * d.n * sizeof(double) + (size_t)((d.P + 3) & ~3) * 2 + (size_t)((d.P + 7) & ~7); }
+size_t egg_collide_smem(const EggDev& d) { return (size_t)17 * d.n * sizeof(double) + (size_t)((d.P + 3) & ~3) * 2 + (size_t)((d.P + 7) & ~7); }
 
 cudaError_t egg_launch_collide(const EggDev& d, cudaStream_t s) {
   const size_t smem = egg_collide_smem(d);

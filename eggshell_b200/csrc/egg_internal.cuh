@@ -3,7 +3,7 @@
 // HBM layout (FP64, indices int32), W worlds of n bodies, nj joints, capacity maxc contacts:
 //   dyn    [W][18][n]   p(3) R(9, row-major) v(3) w(3)          Body state, body.h:79-84
 //   stat   [W][16][n]   1/m, (R I_b R^T)^-1 (9), f_ext (6)      ensembles.cc:202-222 (frozen at init)
-//   bpar   [W][13][n]   side(3) m I_b(9)                        body.h:81,85,91
+//   bpar   [W][14][n]   side(3) m I_b(9) shape                  body.h:81,85,91 (shape: 0 box, 1 sphere, 2 capsule; side = dims)
 //   joints [W][nj] i0,i1 ; jc [W][6][nj] c0(3) c1(3)            joints.h:26-28
 //   contacts: c_i0,c_i1,c_code [W][maxc]; c_geom [W][7][maxc] pos(3) nrm(3) depth
 //   records [W][nrec] x 240 B in dependency-level order; inside one level chunk (<= 32 blocks,
@@ -19,7 +19,7 @@
 
 #define EGG_DYN 18
 #define EGG_STAT 16
-#define EGG_BPAR 13
+#define EGG_BPAR 14
 #define EGG_REC 30          // doubles per constraint record (15 x 16-byte pieces = 240 B)
 #define EGG_PIECES 15
 #define EGG_MAX_POLY 12

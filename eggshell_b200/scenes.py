@@ -185,11 +185,58 @@ def cairn(W, rocks=4, xb=(-0.2, 0.2), yb=(-0.2, 0.2), zb=(1.0, 8.0), seed=7, dt=
     return s
 
 
+def hinge(i0, i1, anchor0, anchor1, axis0, axis1, half_span=0.1):
+    """A hinge between bodies i0 and i1 as TWO ball-and-socket joints on the hinge axis (the
+    reference's only joint type is the 3-row ball joint, joints.h:31; two of them at anchor +-
+    half_span * axis leave exactly the rotation about the axis free; the sixth row is redundant and
+    is absorbed by cfm).  anchors / axes are given in each body's own frame.  Returns the two
+    (i0, i1, c0, c1) tuples to append to a scene's joint lists."""
+    a0, a1 = np.asarray(anchor0, float), np.asarray(anchor1, float)
+    u0, u1 = np.asarray(axis0, float), np.asarray(axis1, float)
+    u0, u1 = u0 / np.linalg.norm(u0), u1 / np.linalg.norm(u1)
+    return [(i0, i1, a0 - half_span * u0, a1 - half_span * u1), (i0, i1, a0 + half_span * u0, a1 + half_span * u1)]
+
+
+def rounds(W, seed=6000, dt=0.005):
+    """Mixed colliders (north_star (a): box / sphere / capsule vs ground): 2 boxes, 3 spheres and 3
+    capsules per world dropped onto the ground from small heights, two of the spheres overlapping
+    (sphere-sphere contact), plus a door: box 1 hinged to box 0 about a vertical axis."""
+    n = 8
+    s = _base(W, n)
+    rng = np.random.default_rng(seed)
+    shape = np.array([0, 0, 1, 1, 1, 2, 2, 2], dtype=np.int32)
+    dims = np.tile(np.array([[0.3, 0.3, 0.3], [0.3, 0.3, 0.3], [0.12, 0, 0], [0.15, 0, 0], [0.1, 0, 0],
+                             [0.08, 0.3, 0], [0.1, 0.2, 0], [0.06, 0.4, 0]]), (W, 1, 1))
+    x = np.array([0.0, 0.32, 1.0, 1.2, 2.0, 3.0, 4.0, 5.0])
+    s["p"][:, :, 0] = x[None, :] + rng.uniform(-0.01, 0.01, size=(W, n))
+    s["p"][:, :, 1] = rng.uniform(-0.01, 0.01, size=(W, n))
+    s["p"][:, :, 2] = np.array([0.149, 0.149, 0.118, 0.149, 0.099, 0.2, 0.15, 0.1])[None, :] + rng.uniform(0, 2e-3, size=(W, n))
+    q = rng.normal(size=(W, n, 4))
+    q /= np.linalg.norm(q, axis=-1, keepdims=True)
+    s["R"] = quat_to_mat(q)
+    s["R"][:, :2] = np.eye(3)                       # the two hinged boxes start axis-aligned
+    s["p"][:, :2, 1] = 0.0
+    s["p"][:, 0, 0] = 0.0; s["p"][:, 1, 0] = 0.32
+    s["p"][:, 1, 2] = s["p"][:, 0, 2]               # the hinge anchors coincide exactly
+    s["v"] = rng.uniform(-0.2, 0.2, size=(W, n, 3))
+    s["v"][:, :2] = 0.0
+    s["w"] = rng.uniform(-0.5, 0.5, size=(W, n, 3))
+    s["w"][:, :2] = 0.0
+    s["I"] = np.tile(np.eye(3) * 0.01, (W, n, 1, 1))
+    js = hinge(0, 1, (0.16, 0.0, 0.0), (-0.16, 0.0, 0.0), (0, 0, 1), (0, 0, 1), half_span=0.1)
+    s.update(nj=2, i0=np.array([j[0] for j in js], dtype=np.int32), i1=np.array([j[1] for j in js], dtype=np.int32),
+             c0=np.tile(np.array([j[2] for j in js]), (W, 1, 1)), c1=np.tile(np.array([j[3] for j in js]), (W, 1, 1)),
+             shape=np.tile(shape, (W, 1)), dims=dims, dt=dt, name="rounds")
+    return s
+
+
 def make_batch(scene, **kw):
     """Creates, fills and initialises a ``Batch`` from a scene dict."""
     from .batch import Batch
     b = Batch(scene["W"], scene["n"], scene["nj"], **kw)
     b.set_bodies(scene["p"], scene["R"], scene["v"], scene["w"], scene["m"], scene["I"])
+    if "shape" in scene:
+        b.set_shapes(scene["shape"], scene["dims"])
     if scene["nj"]:
         b.set_joints(scene["i0"], scene["i1"], scene["c0"], scene["c1"])
     b.init()

@@ -107,6 +107,15 @@ void egg_destroy(egg_batch* b);
  * (0.3,0.3,0.3 as body.h:91). */
 int egg_set_bodies(egg_batch* b, const double* p, const double* R, const double* v, const double* w,
                    const double* m, const double* I_body, const double* side);
+/* Colliders other than the reference's box (BASELINE.json north_star (a); the reference only draws
+ * spheres and capsules, model.h:16-25, so the contact rules are this project's, defined by
+ * oracle/orc_collision.h: parity unpinned).  shape[W][n]: 0 box (dims = side lengths, the default),
+ * 1 sphere (dims[0] = radius), 2 capsule (dims[0] = radius, dims[1] = length of the axis segment along
+ * the body's z axis); dims[W][n][3].  Ground contacts: the lowest point of every (end) sphere below
+ * z = 0; pairs: box-box (the reference's SAT) and sphere-sphere (one contact, code 17); other
+ * collider pairs generate no contacts.  Call after egg_set_bodies; mass and inertia stay the caller's. */
+int egg_set_shapes(egg_batch* b, const int* shape, const double* dims);
+
 /* Dynamic state only (SetP/SetR/SetV/SetW_GlobalFrame, body.h:64-71).  The host-to-device copies
  * are asynchronous on the batch stream: when the arrays live in pinned memory (egg_host_alloc) the
  * call returns before they have been read, so keep them unchanged until the next synchronising

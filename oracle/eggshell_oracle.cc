@@ -198,6 +198,10 @@ void orc_world_set_bodies(void* wp, int n, const double* p, const double* R, con
     if (side) b.side = v3(side + 3 * i);
   }
 }
+void orc_world_set_shapes(void* wp, const int* shape, const double* dims) {
+  World& W = *(World*)wp;
+  for (int i = 0; i < W.n; i++) { W.bodies[i].shape = shape[i]; W.bodies[i].side = v3(dims + 3 * i); }
+}
 void orc_world_set_state(void* wp, const double* p, const double* R, const double* v, const double* w) {
   World& W = *(World*)wp;
   for (int i = 0; i < W.n; i++) {

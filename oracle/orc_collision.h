@@ -274,6 +274,51 @@ inline bool collide_box_and_ground(const Vec3& center, const Mat3& rotation, con
   return retval;
 }
 
+// ---- Spheres and capsules (BASELINE.json north_star (a); NOT in the reference, whose only collider
+// is the box, body.h:90-91 -- the reference merely has DrawSphere / DrawCapsule, model.h:16-25).
+// Defined here by analogy with CollideBoxAndGround: "parity unpinned", the oracle is the definition.
+// Shape codes: 0 box (dims = side lengths), 1 sphere (dims[0] = radius), 2 capsule (dims[0] = radius,
+// dims[1] = length of the axis segment, along the body's z axis).
+// Ground: the lowest point of every sphere (a capsule = two end spheres, -z end first) is a contact
+// when it is below z = 0: position = that point, normal +z, depth = -z, as for a box vertex.
+inline bool collide_round_and_ground(int shape, const Vec3& center, const Mat3& rotation, const Vec3& dims,
+                                     std::vector<ContactGeometry>* contacts) {
+  bool retval = false;
+  const double r = dims[0];
+  const int ends = (shape == 2) ? 2 : 1;
+  for (int e = 0; e < ends; e++) {
+    Vec3 c = center;
+    if (shape == 2) c = center + rotation.col(2) * (dims[1] * 0.5 * (e == 0 ? -1.0 : 1.0));
+    Vec3 v(c[0], c[1], c[2] - r);
+    if (v[2] < 0) {
+      ContactGeometry g;
+      g.position = v;
+      g.normal = Vec3(0, 0, 1);
+      g.depth = -v[2];
+      contacts->push_back(g);
+      retval = true;
+    }
+  }
+  return retval;
+}
+// Sphere - sphere: one contact at the middle of the overlap, normal out of sphere 1 (the box-box
+// convention, collision.cc:325-387), depth = r1 + r2 - distance > 0; code 17.
+inline bool collide_spheres(const Vec3& c1, double r1, const Vec3& c2, double r2, CollisionInfo* info,
+                            std::vector<ContactGeometry>* contacts) {
+  Vec3 d = c2 - c1;
+  const double dist = norm(d);
+  const double depth = (r1 + r2) - dist;
+  if (!(depth > 0)) return false;
+  Vec3 n = (dist > 0) ? d / dist : Vec3(0, 0, 1);
+  ContactGeometry g;
+  g.position = c1 + n * (r1 - depth * 0.5);
+  g.normal = n;
+  g.depth = depth;
+  contacts->push_back(g);
+  info->depth = depth; info->separating_axis = n; info->code = 17;
+  return true;
+}
+
 // collision.cc:443-473 (test helpers): slow-but-sure 15-axis separation test.
 inline bool boxes_separated_by_axis(const Box& b1, const Box& b2, const Vec3& axis) {
   double span1 = b1.halfside[0] * std::fabs(dot(axis, b1.R.col(0))) +

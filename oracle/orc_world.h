@@ -16,7 +16,8 @@ struct Body {                     // body.h:13-96
   double m = 1;
   Mat3 R = Mat3::identity();
   Mat3 I;                         // body frame
-  Vec3 side = Vec3(0.3, 0.3, 0.3);   // body.h:91
+  Vec3 side = Vec3(0.3, 0.3, 0.3);   // body.h:91 (box side lengths; sphere / capsule dims, orc_collision.h)
+  int shape = 0;                  // 0 box (the reference's only collider), 1 sphere, 2 capsule
   Mat3 I_g() const { return R * I * transpose(R); }   // body.h:58, (R*I)*R^T
 };
 // body.cc:19-36
@@ -205,7 +206,8 @@ inline void update_contacts(World& W) {
   for (int i = 0; i < W.n; i++) {
     cgs.clear();
     const Body& b = W.bodies[i];
-    collide_box_and_ground(b.p, b.R, b.side, &cgs);
+    if (b.shape == 0) collide_box_and_ground(b.p, b.R, b.side, &cgs);
+    else collide_round_and_ground(b.shape, b.p, b.R, b.side, &cgs);
     W.ground_count[i] = (int)cgs.size();
     for (const auto& cg : cgs) { Contact c; c.i0 = -1; c.i1 = i; c.cg = cg; W.contacts.push_back(c); }
   }
@@ -217,7 +219,12 @@ inline void update_contacts(World& W) {
       Box b1{W.bodies[i].p, W.bodies[i].R, W.bodies[i].side * 0.5};
       Box b2{W.bodies[j].p, W.bodies[j].R, W.bodies[j].side * 0.5};
       tests++;
-      if (collide_boxes(b1, b2, &ci, &cgs)) {
+      const int s1 = W.bodies[i].shape, s2 = W.bodies[j].shape;
+      bool hit = false;
+      if (s1 == 0 && s2 == 0) hit = collide_boxes(b1, b2, &ci, &cgs);
+      else if (s1 == 1 && s2 == 1) hit = collide_spheres(W.bodies[i].p, W.bodies[i].side[0], W.bodies[j].p, W.bodies[j].side[0], &ci, &cgs);
+      // other shape pairs: no pairwise narrowphase (documented limitation)
+      if (hit) {
         W.pair_hit_i.push_back(i); W.pair_hit_j.push_back(j);
         W.pair_hit_code.push_back(ci.code); W.pair_hit_count.push_back((int)cgs.size());
       }

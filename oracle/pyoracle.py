@@ -246,6 +246,11 @@ class World:
         s = None if side is None else _d(side)
         lib().orc_world_set_bodies(self.h, n, _p(p), _p(R), _p(v), _p(w), _p(m), _p(I), None if s is None else _p(s))
 
+    def set_shapes(self, shape, dims):
+        shape = np.ascontiguousarray(shape, dtype=np.int32)
+        dims = _d(dims)
+        lib().orc_world_set_shapes(self.h, _pi(shape), _p(dims))
+
     def set_state(self, p, R, v, w):
         p, R, v, w = [_d(x) for x in (p, R, v, w)]
         lib().orc_world_set_state(self.h, _p(p), _p(R), _p(v), _p(w))

@@ -8,6 +8,8 @@ from oracle import pyoracle as O
 def oracle_world(scene, w, **params):
     W = O.World()
     W.set_bodies(scene["p"][w], scene["R"][w], scene["v"][w], scene["w"][w], scene["m"][w], scene["I"][w])
+    if "shape" in scene:
+        W.set_shapes(scene["shape"][w], scene["dims"][w])
     if scene["nj"]:
         W.set_joints(scene["i0"], scene["i1"], scene["c0"][w], scene["c1"][w])
     W.set_params(**params)

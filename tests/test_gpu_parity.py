@@ -70,6 +70,25 @@ def test_pgs_fixed_k20_stepwise(name, W, steps):
     print(name, "K=20 worst", worst)
 
 
+def test_rounds_sphere_capsule_hinge_stepwise():
+    """SURVEY row f4 / north_star (a): sphere and capsule colliders against the ground, a
+    sphere-sphere pair, and a hinge (two ball joints on the axis) between two boxes, stepwise
+    against the oracle (which DEFINES these contacts: the reference has boxes only -- parity
+    unpinned).  Contact lists, codes (17 = sphere-sphere) and order bit-exact, state within 1e-9."""
+    import eggshell_b200 as E
+    scene = E.scenes.rounds(6)
+    worst = _stepwise(scene, 8, list(range(6)), dict(solver=E.SOLVER_PGS, k_max=100), dict(solver=1, k_max=100), lam_tol=1e-8)
+    print("rounds worst", worst)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=100, taps=True)
+    b.step(scene["dt"], n_steps=3)
+    con, ph = b.contacts(), b.pair_hits()
+    for wi in range(6):
+        nc = con["count"][wi]
+        assert (con["code"][wi, :nc] == 17).sum() == 1 and (con["i0"][wi, :nc] == -1).sum() >= 5
+    assert int(np.bitwise_or.reduce(b.status()["status"])) == 0
+    b.close()
+
+
 def test_cairn_pgs_falling():
     import eggshell_b200 as E
     scene = E.scenes.cairn(16, rocks=4, zb=(0.2, 1.0), seed=11)
