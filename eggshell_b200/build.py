@@ -18,6 +18,7 @@ UNITS = [
     ("egg_pgs.cu", []),
     ("egg_iter.cu", []),
     ("egg_pgs_stream.cu", []),
+    ("egg_pgs_runs.cu", []),
     ("egg_dense.cu", ["-fmad=false"]),
     ("egg_capi.cu", []),
 ]

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 cudaError_t egg_launch_solve_dense(const EggDev& d, double dt, cudaStream_t s, void* scratch, size_t scratch_bytes);
 size_t egg_dense_scratch_bytes(const EggDev& d);
@@ -183,6 +184,7 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   // The PGS solver streams group-interleaved records (format 1, egg_pgs_stream.cu); the dense path,
   // Jacobi / SOR and the relaxation read per-world 240-byte records (format 0, egg_pgs.cu).
   d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS) ? 1 : 0;
+  d.rmax = 1;
   // the group-stream assembly keeps u16 level tables of 2 (n + 4 nrec) bytes per world in shared memory
   if (d.rec_fmt && d.nrec > 24000) { g_err = "PGS: more than 24000 constraint slots per world (n_joints + max_contacts) are not supported"; egg_destroy(b); return EGG_ERR_UNSUPPORTED; }
   if (d.rec_fmt) {
@@ -193,6 +195,12 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
     DA(d.rec, egg_stream_rec_bytes(W, d.nrec, d.lpw) / sizeof(double));
     DA(d.c_pos, (size_t)W * d.nrec);
     DA(d.st_cnt, (size_t)W * d.nrec);
+    // run format (egg_pgs_runs.cu): FP64 records, at most 8 lanes per world; whether the bodies are
+    // isotropic (its other condition) is known after egg_init, so the choice is made at the first step
+    if (dsc->precision == 64 && d.lpw <= 8) {
+      DA(d.st_runs, (size_t)W * d.nrec);
+      d.run_cap = egg_run_cap(d);
+    }
     DA(d.round_off, (size_t)groups * (d.nrec + 1));
     DA(d.grp_info, (size_t)groups * 4);
   } else {
@@ -230,7 +238,7 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
     struct { const char* what; size_t need; } req[4] = {
         {"narrowphase (egg_collide_kernel)", egg_collide_smem(d)},
         {"row assembly", d.rec_fmt ? (size_t)0 : egg_assemble_smem(d)},
-        {"PGS group stream", d.rec_fmt ? egg_stream_smem(d) : (size_t)0},
+        {"PGS group stream", d.rec_fmt ? (d.st_runs ? std::max(egg_stream_smem(d), egg_runs_smem(d)) : egg_stream_smem(d)) : (size_t)0},
         {"Jacobi / SOR", (dsc->solver == EGG_SOLVER_JACOBI || dsc->solver == EGG_SOLVER_SOR) ? egg_iter_smem(d) : (size_t)0}};
     for (auto& r : req)
       if (r.need > (size_t)lim) {
@@ -532,6 +540,7 @@ int egg_step(egg_batch* b, double dt, int integrator, int n_steps) {
     b->dev.iso = !(flag & 1) ? 0 : ((flag & 2) ? 2 : 1);   // 0 general, 1 isotropic, 2 isotropic and uniform
     if (getenv("EGG_PGS_ISO") && atoi(getenv("EGG_PGS_ISO")) < b->dev.iso) b->dev.iso = atoi(getenv("EGG_PGS_ISO"));
     b->iso_known = true;
+    b->dev.rmax = egg_runs_rmax(b->dev);   // run format of the PGS stream for isotropic bodies, else one block per lane and stage
   }
   for (int s = 0; s < n_steps; s++) {
     cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};

@@ -81,6 +81,10 @@ struct EggDev {
   // group-stream assembly of the default PGS variant (egg_pgs_stream.cu)
   int blkb;                   // stream bytes per block: 32 (multipliers) + 208 (FP64 record) or 112 (precision = 32 record)
   int lpw;                    // lanes per world = stage cap; G = 32 / lpw worlds share a warp and a record stream
+  int rmax;                   // 1: one block per lane and stage (egg_pgs_stream.cu); > 1: a lane carries a run of up to rmax
+                              //    consecutive blocks on the same body pair through a stage (egg_pgs_runs.cu)
+  unsigned* st_runs;          // [W][nrec] run lengths of a world's stage, 4 bits per lane of the world (run format only, else null)
+  int run_cap;                // runs per world and stage of the run format (<= lpw; bounded by the staging buffer)
   int* c_pos;                 // [W][nrec] stage << 8 | index inside the stage, per constraint
   unsigned char* st_cnt;      // [W][nrec] blocks per stage
   unsigned* round_off;        // [groups][nrec+1] byte offset of every round inside the group stream
@@ -136,6 +140,11 @@ cudaError_t egg_launch_clear_contacts(const EggDev& d, cudaStream_t s);
 cudaError_t egg_launch_assemble(const EggDev& d, double dt, cudaStream_t s);
 cudaError_t egg_launch_solve_pgs(const EggDev& d, double dt, cudaStream_t s);
 cudaError_t egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s);
+cudaError_t egg_launch_solve_pgs_runs(const EggDev& d, double dt, cudaStream_t s);
+int egg_run_cap(const EggDev& d);
+int egg_runs_rmax(const EggDev& d);
+size_t egg_runs_smem(const EggDev& d);
+cudaError_t egg_launch_assemble_runs_tail(const EggDev& d, double dt, cudaStream_t s);
 cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s);
 size_t egg_stream_rec_bytes(int W, int nrec, int lpw);
 int egg_stream_blkb(int precision);

@@ -46,120 +46,21 @@
 // replace Ensemble::ComputeJ / rhs (ensembles.cc:38-87,156-171,563-570) via egg_record.cuh.
 #include "egg_internal.cuh"
 #include "egg_record.cuh"
-#include <math_constants.h>
+#include "egg_stream.cuh"
 #include <cstdlib>
 
 namespace {
-
-#define kInf CUDART_INF
-// Two record formats (layouts below): FP64 records of 26 doubles = 208 B = 13 x 16 B, and the opt-in
-// precision = 32 format of 24 floats + the packed word = 112 B = 7 x 16 B (both odd multiples of
-// 16 B: conflict-free 128-bit shared-memory reads at these strides).
-constexpr int SREC = 26;            // doubles per FP64 stream record
-constexpr int RECB64 = SREC * 8;    // 208
-constexpr int RECB32 = 112;
-constexpr int LAMB = 32;            // bytes of one block's multipliers (3 doubles + pad = one sector)
-constexpr int BLKB_MAX = RECB64 + LAMB;   // stream bytes per block, FP64 records (allocation bound)
-
-__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_tx(unsigned bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// records stream through L2 once per sweep: evict-first, so that the small per-body arrays stay
-__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar, unsigned long long pol) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar), "l"(pol)
-               : "memory");
-}
-__device__ __forceinline__ unsigned long long policy_evict_first() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ unsigned long long policy_evict_last() {
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ double2 ldg_keep(const double2* p, unsigned long long pol) {   // read-only, L2 evict-last
-  double2 r;
-  asm volatile("ld.global.nc.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-  return r;
-}
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n"
-      "LAB_WAIT:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra LAB_DONE;\n\t"
-      "bra LAB_WAIT;\n"
-      "LAB_DONE:\n\t}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-
-// Stream record (26 doubles): [0..8] Rc, [9..11] r0, [12..14] r1, [15..17] D off-diagonal,
-// [18..20] 1/(D+cfm), [21..23] rhs, [24] packed (i0+1 | (i1+1) << 10 | kind << 20 | original
-// constraint index << 21), [25] spare.  The multipliers are NOT in the record: a round keeps them
-// in one contiguous array of 32-byte sectors in front of its records, so that the write-back of
-// a warp-stage is a run of consecutive full sectors.  (With the multipliers inside each record
-// the scattered 32-byte stores alone cost 40 % of the stream: tools/micro/stream_bench measures
-// 4.1 TB/s with them against 6.2 read-only and 5.6 with the compact array; and partial-sector
-// stores additionally made L2 fetch every sector it merged: +8 GB reads per launch, profiles/r1f.)
-// precision = 32 record (112 B): the same 24 numbers as floats (96 B), then the packed word and 8
-// spare bytes.  The kernel widens them to double as it reads; multipliers, accumulators and all
-// arithmetic stay FP64.
-// Inside the kernel the 24 numbers of either format are fld[0..23]:
-#define RC0 fld[0]
-#define RC1 fld[1]
-#define RC2 fld[2]
-#define RC3 fld[3]
-#define RC4 fld[4]
-#define RC5 fld[5]
-#define RC6 fld[6]
-#define RC7 fld[7]
-#define RC8 fld[8]
-#define R0X fld[9]
-#define R0Y fld[10]
-#define R0Z fld[11]
-#define R1X fld[12]
-#define R1Y fld[13]
-#define R1Z fld[14]
-#define DO0 fld[15]
-#define DO1 fld[16]
-#define DO2 fld[17]
-#define IA0 fld[18]
-#define IA1 fld[19]
-#define IA2 fld[20]
-#define RH0 fld[21]
-#define RH1 fld[22]
-#define RH2 fld[23]
-
-__device__ __forceinline__ void st_sector(double* p, double a, double b, double c, double e) {   // one aligned 32-byte store
-  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(e) : "memory");
-}
-
-
-constexpr int HDRB = 64;      // round header bytes (keeps the multiplier sectors 32-byte aligned)
-// bytes of a round with `total` blocks: header, multipliers, records, padded to a sector
-__host__ __device__ inline unsigned round_bytes(int total, int blkb) { return (unsigned)(HDRB + blkb * total + 31) & ~31u; }
-constexpr int HDR_NEXT = 40;  // byte 40: total blocks of the next round (cyclic); byte 41: of the one after (unused)
-
-__host__ __device__ inline size_t group_stride_bytes(int nrec, int G) { return ((size_t)nrec * ((size_t)BLKB_MAX * G + HDRB + 32) + 255) & ~(size_t)255; }
 
 // ---------------------------------------------------------------------------------------------
 // Assembly 1/3: dependency levels and stages of one world (one warp per world, lane 0 scans).
 //   level(c) = 1 + max level of earlier constraints sharing a body  (constraints in reference
 //   order: joints, then contacts, ensembles.cc:234-239); a level is cut into stages of <= cap.
-// Out: c_pos[c] = stage << 8 | index inside the stage, st_cnt[stage], n_levels = #stages.
-__global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, int wpc) {
+// rm > 1 (egg_pgs_runs.cu): the unit is a RUN of up to rm consecutive constraints on the same
+//   ordered body pair (the contacts of one manifold, ensembles.cc:449-473): they would occupy
+//   consecutive levels anyway, and one lane can carry both bodies' accumulators through them.
+// Out: c_pos[c] = stage << 8 | lane << 3 | index inside the run, st_cnt[stage] (rm == 1) or
+//   st_runs[stage] (4 bits per lane: run length), n_levels = #stages.
+__global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, int wpc, int rm) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int wl = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int w = blockIdx.x * wpc + wl;
@@ -168,32 +69,55 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
   const size_t per = (size_t)(n + 4 * nrec + 2 + 7) & ~(size_t)7;
   unsigned short* blast = reinterpret_cast<unsigned short*>(sm_raw) + (size_t)wl * per;
   unsigned short* lev = blast + n;
-  unsigned short* pos = lev + nrec;
+  unsigned short* pos = lev + nrec;     // unit index inside its level (bits 0..11 when rm > 1: | k << 12 | last-of-run << 15)
   unsigned short* lcnt = pos + nrec;
   unsigned short* lstage = lcnt + nrec + 1;
   if (wl >= wpc || w >= d.W) return;
   const int nc = nj + d.c_count[w];
   const int* c_i0 = d.c_i0 + (size_t)w * d.maxc;
   const int* c_i1 = d.c_i1 + (size_t)w * d.maxc;
-  for (int b = lane; b < n; b += 32) blast[b] = 0;          // level + 1 of the last constraint on the body (0 = none)
+  for (int b = lane; b < n; b += 32) blast[b] = 0;          // level + 1 of the last unit on the body (0 = none)
   for (int c = lane; c <= nc; c += 32) lcnt[c] = 0;
+  if (rm > 1) {
+    // pos[c] = 1: contact c may extend the run of contact c - 1: same ordered body pair and bit-identical
+    // normal (one manifold, or one body's ground contacts), so the two share the contact frame
+    const double* gm = d.c_geom + (size_t)w * 7 * d.maxc;
+    for (int c = lane; c < nc; c += 32) {
+      bool same = false;
+      if (c > nj) {
+        const int k = c - nj;
+        same = c_i0[k] == c_i0[k - 1] && c_i1[k] == c_i1[k - 1];
+        for (int q = 3; q < 6 && same; q++) same = __double_as_longlong(gm[(size_t)q * d.maxc + k]) == __double_as_longlong(gm[(size_t)q * d.maxc + k - 1]);
+      }
+      pos[c] = same ? 1 : 0;
+    }
+  }
   __syncwarp();
-  int nl = 0;
+  int nl = 0, ns = 0;
   if (lane == 0) {
+    int pl = 0, pp = 0, plen = 0;
     for (int c = 0; c < nc; c++) {
       int i0, i1;
       if (c < nj) { i0 = d.j_i0[(size_t)w * nj + c]; i1 = d.j_i1[(size_t)w * nj + c]; }
       else { i0 = __ldg(c_i0 + c - nj); i1 = __ldg(c_i1 + c - nj); }
+      if (rm > 1 && pos[c] != 0 && plen < rm) {                         // extends the previous run
+        pos[c - 1] &= 0x7fff;                                            // the previous block is no longer the last
+        lev[c] = (unsigned short)pl;
+        pos[c] = (unsigned short)(pp | (plen << 12) | 0x8000);
+        plen++;
+        continue;
+      }
       int l = 0;
       if (i0 >= 0) l = blast[i0];
       if (i1 >= 0) l = max(l, (int)blast[i1]);
       if (i0 >= 0) blast[i0] = (unsigned short)(l + 1);
       if (i1 >= 0) blast[i1] = (unsigned short)(l + 1);
       lev[c] = (unsigned short)l;
-      pos[c] = lcnt[l]++;
+      pp = lcnt[l]++;
+      pos[c] = (unsigned short)((rm > 1) ? (pp | 0x8000) : pp);
+      pl = l; plen = 1;
       nl = max(nl, l + 1);
     }
-    int ns = 0;
     unsigned char* sc = d.st_cnt + (size_t)w * nrec;
     for (int l = 0; l < nl; l++) {
       const int cnt = lcnt[l];
@@ -202,11 +126,24 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
     }
     d.n_levels[w] = ns;
   }
+  ns = __shfl_sync(0xffffffffu, ns, 0);
   __syncwarp();
   int* cp = d.c_pos + (size_t)w * nrec;
-  for (int c = lane; c < nc; c += 32) {
-    const int p = pos[c];
-    cp[c] = ((lstage[lev[c]] + p / cap) << 8) | (p % cap);
+  if (rm > 1) {
+    unsigned* sr = d.st_runs + (size_t)w * nrec;
+    for (int t = lane; t < ns; t += 32) sr[t] = 0u;
+    __syncwarp();
+    for (int c = lane; c < nc; c += 32) {
+      const int pv = pos[c], p = pv & 0xfff, k = (pv >> 12) & 7;
+      const int stg = lstage[lev[c]] + p / cap, ln = p % cap;
+      cp[c] = (stg << 8) | (ln << 3) | k;
+      if (pv & 0x8000) atomicOr(sr + stg, (unsigned)(k + 1) << (4 * ln));   // the last block of a run knows its length
+    }
+  } else {
+    for (int c = lane; c < nc; c += 32) {
+      const int p = pos[c];
+      cp[c] = ((lstage[lev[c]] + p / cap) << 8) | ((p % cap) << 3);
+    }
   }
 }
 
@@ -294,7 +231,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : 4) egg_records_kernel(Eg
     else { i0 = c_i0[c - nj]; i1 = c_i1[c - nj]; }
     double v[EGG_REC];
     egg_build_record(d, w, c, i0, i1, sdyn, sst, su, geom, dt, true, v);
-    const int p = cp[c], stg = p >> 8, idx = p & 255;
+    const int p = cp[c], stg = p >> 8, idx = (p >> 3) & 31;
     const unsigned ro = roff[stg];
     const unsigned start = gs[ro + sub];
     const int kind = __double2hiint(v[REC_META]);
@@ -506,13 +443,13 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         const bool contact = ((pk >> 20) & 1u) == KIND_CONTACT;
         const double lo01 = contact ? -1.0 : -kInf, hi01 = contact ? 1.0 : kInf, lo2 = contact ? 0.0 : -kInf;
         double n0 = x0 + e0 * IA0;
-        n0 = fmin(fmax(n0, lo01), hi01);
+        n0 = clamp_sel(n0, lo01, hi01);
         d0 = n0 - x0;
         double n1 = x1 + (e1 - DO0 * d0) * IA1;
-        n1 = fmin(fmax(n1, lo01), hi01);
+        n1 = clamp_sel(n1, lo01, hi01);
         d1 = n1 - x1;
         double n2 = x2 + ((e2 - DO1 * d0) - DO2 * d1) * IA2;
-        n2 = fmax(n2, lo2);
+        n2 = (n2 < lo2) ? lo2 : n2;
         d2 = n2 - x2;
         st_sector(reinterpret_cast<double*>(gs + lam_off), n0, n1, n2, 0.0);
       }
@@ -701,45 +638,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         stt[7] = d.n_levels[w];
         d.resid[w] = err;
       }
-      // v' = v + dt (M^-1 f + a); p += dt (v+v')/2; R <- WtoQ((w+w')/2, dt) R  (ensembles.cc:535,572-591)
-      double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
-      const double* st = d.stat + (size_t)w * EGG_STAT * n;
-      bool bad = false;
-      for (int b = sl; b < n; b += LPW) {
-        const double* q = sb + b * 6;
-        const double mi = __ldg(st + b);
-        double Ii[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) Ii[c] = __ldg(st + (1 + c) * n + b);
-        d3 fl = mk3(st[10 * n + b], st[11 * n + b], st[12 * n + b]);
-        d3 ft = mk3(st[13 * n + b], st[14 * n + b], st[15 * n + b]);
-        d3 v = mk3(dyn[12 * n + b], dyn[13 * n + b], dyn[14 * n + b]);
-        d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
-        d3 vn = v + dt * (fl * mi + mk3(q[0], q[1], q[2]));
-        d3 wn = wv + dt * (mmulv(Ii, ft) + mk3(q[3], q[4], q[5]));
-        d3 vmid = (v + vn) / 2.0, wmid = (wv + wn) / 2.0;
-        d3 p = mk3(dyn[b], dyn[n + b], dyn[2 * n + b]) + dt * vmid;
-        double z2 = dot3(wmid, wmid);
-        d3 axis = (z2 > 0) ? wmid / sqrt(z2) : wmid;
-        double ha = 0.5 * (norm3(wmid) * dt);
-        double qw = cos(ha), sn = sin(ha);
-        double qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
-        double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
-        double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-        double Q[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
-        double R[9], Rn[9];
-#pragma unroll
-        for (int c = 0; c < 9; c++) R[c] = dyn[(3 + c) * n + b];
-        mmulm(Q, R, Rn);
-        dyn[b] = p.x; dyn[n + b] = p.y; dyn[2 * n + b] = p.z;
-#pragma unroll
-        for (int c = 0; c < 9; c++) dyn[(3 + c) * n + b] = Rn[c];
-        dyn[12 * n + b] = vn.x; dyn[13 * n + b] = vn.y; dyn[14 * n + b] = vn.z;
-        dyn[15 * n + b] = wn.x; dyn[16 * n + b] = wn.y; dyn[17 * n + b] = wn.z;
-        double chk = p.x + p.y + p.z + vn.x + vn.y + vn.z + wn.x + wn.y + wn.z;
-        bad |= !(fabs(chk) < 1e300);
-      }
-      if (bad) atomicOr(&d.status[w], 16 /*EGG_ST_NONFINITE*/);
+      stream_integrate_world(d, w, sb, sl, LPW, dt);
     }
     __syncwarp();
   }
@@ -839,8 +738,9 @@ cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t 
     const size_t smem = wpc * per;
     if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (e != cudaSuccess) return e;
-    egg_schedule_kernel<<<(d.W + wpc - 1) / wpc, 128, smem, s>>>(d, d.lpw, wpc);
+    egg_schedule_kernel<<<(d.W + wpc - 1) / wpc, 128, smem, s>>>(d, d.rmax > 1 ? egg_run_cap(d) : d.lpw, wpc, d.rmax);
   }
+  if (d.rmax > 1) return egg_launch_assemble_runs_tail(d, dt, s);   // run headers and run-format records (egg_pgs_runs.cu)
   const int ngroups = (d.W + G - 1) / G;
   egg_rounds_kernel<<<(ngroups + 3) / 4, 128, 0, s>>>(d, G);
   const size_t smem = (size_t)(EGG_DYN + EGG_STAT + 6) * d.n * sizeof(double);
@@ -857,6 +757,7 @@ cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t 
 }
 
 cudaError_t egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s) {
+  if (d.rmax > 1) return egg_launch_solve_pgs_runs(d, dt, s);
   if (d.iso == 2) return launch_nbuf<12, 2>(d, dt, s);
   if (d.iso == 1) return launch_nbuf<12, 1>(d, dt, s);
   return launch_nbuf<8, 0>(d, dt, s);

@@ -8,7 +8,9 @@
 
 // Eigen 3.3 Quaternion::FromTwoVectors(normal, z).toRotationMatrix()  (utils.cc:233-236).  The
 // exactly anti-parallel case uses the same pinned rule as the oracle (orc_linalg.h).
-__device__ inline void egg_align_to_z(d3 nrm, double* R) {
+// egg_align_quat: the quaternion (w, x, y, z); egg_quat_rot: its rotation matrix (the run-format
+// records of egg_pgs_runs.cu store the quaternion and rebuild the matrix with the same expressions).
+__device__ inline void egg_align_quat(d3 nrm, double* q) {
   double z2 = dot3(nrm, nrm);
   d3 v0 = (z2 > 0) ? nrm / sqrt(z2) : nrm;
   double c = v0.z;   // dot(v1 = (0,0,1), v0)
@@ -33,6 +35,9 @@ __device__ inline void egg_align_to_z(d3 nrm, double* R) {
     qx = ax.x * invs; qy = ax.y * invs; qz = ax.z * invs;
     qw = s * 0.5;
   }
+  q[0] = qw; q[1] = qx; q[2] = qy; q[3] = qz;
+}
+__device__ __forceinline__ void egg_quat_rot(double qw, double qx, double qy, double qz, double* R) {
   double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
   double twx = tx * qw, twy = ty * qw, twz = tz * qw;
   double txx = tx * qx, txy = ty * qx, txz = tz * qx;
@@ -40,6 +45,11 @@ __device__ inline void egg_align_to_z(d3 nrm, double* R) {
   R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
   R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
   R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+__device__ inline void egg_align_to_z(d3 nrm, double* R) {
+  double q[4];
+  egg_align_quat(nrm, q);
+  egg_quat_rot(q[0], q[1], q[2], q[3], R);
 }
 
 // u = v/dt + M^-1 f per body (the vector the rhs multiplies J with, ensembles.cc:569-570), computed

@@ -54,7 +54,12 @@ enum egg_quirk {
   EGG_OPT_EXACT_INERTIA = 4,
   /* Not a reference quirk: run the 15-axis SAT on every body pair.  By default pairs whose bounding
    * spheres are clearly apart are culled first (conservative: the colliding-pair list is unchanged). */
-  EGG_OPT_NO_BROADPHASE_CULL = 8
+  EGG_OPT_NO_BROADPHASE_CULL = 8,
+  /* Not a reference quirk: the run format of the PGS record stream (egg_pgs_runs.cu): a lane carries
+   * the consecutive contacts of one manifold through a stage, records shrink to 80 B per block +
+   * 64 B per run.  Same sweep in the same row order; measured faster only for stack-like scenes
+   * (DESIGN.md section 4), so it is opt-in.  Isotropic bodies, FP64 records only (else ignored). */
+  EGG_OPT_PGS_RUNS = 16
 };
 #define EGG_QUIRKS_REFERENCE 3
 
