@@ -15,6 +15,7 @@
 // (collision.cc:189-190,218,249,282,369,419) must see exactly the value the FP64 CPU arithmetic
 // produces, because hit / code / count are compared bit-exactly with the oracle.
 #include "egg_internal.cuh"
+#include <cstdlib>
 #include <cfloat>
 
 namespace {
@@ -586,8 +587,17 @@ size_t egg_collide_smem(const EggDev& d) { return (size_t)17 * d.n * sizeof(doub
 cudaError_t egg_launch_collide(const EggDev& d, cudaStream_t s) {
   const size_t smem = egg_collide_smem(d);
   cudaError_t e = cudaSuccess;
-  if (d.n <= 16) {
+  static const int env_nt = getenv("EGG_COLLIDE_NT") ? atoi(getenv("EGG_COLLIDE_NT")) : 0;   // development override: 64 / 128 / 256
+  // threads per world by its pair count: one warp for small worlds (every barrier and block scan
+  // is paid per warp).  Measured, 131072 x 20 bodies (190 pairs): 3.45 ms at 256 threads, 2.56 at
+  // 128, 1.52 at 64, 1.08 at 32; 16384 x 64 bodies (2016 pairs): 2.81 ms at 256, 3.41 at 128.
+  const int nt = env_nt ? env_nt : (d.P <= 256 ? 32 : (d.P <= 600 ? 64 : (d.P <= 1200 ? 128 : 256)));
+  if (nt == 32) {
+    egg_collide_kernel<32><<<d.W, 32, smem, s>>>(d);
+  } else if (nt == 64) {
     egg_collide_kernel<64><<<d.W, 64, smem, s>>>(d);
+  } else if (nt == 128) {
+    egg_collide_kernel<128><<<d.W, 128, smem, s>>>(d);
   } else {
     static thread_local size_t attr_set = 0;       // the attribute only ever has to grow
     if (smem > 48 * 1024 && smem > attr_set) {

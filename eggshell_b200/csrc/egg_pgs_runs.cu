@@ -671,10 +671,15 @@ cudaError_t egg_launch_assemble_runs_tail(const EggDev& d, double dt, cudaStream
   const int ngroups = (d.W + G - 1) / G;
   egg_rounds_runs_kernel<<<(ngroups + 3) / 4, 128, 0, s>>>(d, G);
   const size_t smem = (size_t)(EGG_DYN + EGG_STAT + 6) * d.n * sizeof(double);
-  if (d.nrec <= 128) {
-    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_runs_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int est = d.nj + 6 * d.n;           // threads per world as in egg_pgs_stream.cu (launch_records)
+  if (est <= 192) {
+    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_runs_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (e != cudaSuccess) return e;
-    egg_records_runs_kernel<64><<<d.W, 64, smem, s>>>(d, dt, G);
+    egg_records_runs_kernel<32><<<d.W, 32, smem, s>>>(d, dt, G);
+  } else if (est <= 768) {
+    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_runs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (e != cudaSuccess) return e;
+    egg_records_runs_kernel<128><<<d.W, 128, smem, s>>>(d, dt, G);
   } else {
     if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_runs_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (e != cudaSuccess) return e;

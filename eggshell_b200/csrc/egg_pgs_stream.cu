@@ -78,6 +78,15 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
   const int* c_i1 = d.c_i1 + (size_t)w * d.maxc;
   for (int b = lane; b < n; b += 32) blast[b] = 0;          // level + 1 of the last unit on the body (0 = none)
   for (int c = lane; c <= nc; c += 32) lcnt[c] = 0;
+  // body indices + 1 of every constraint, staged with coalesced loads: the serial scan below must not
+  // wait for global memory once per constraint (lev[c] is overwritten by the scan, lstage after it)
+  for (int c = lane; c < nc; c += 32) {
+    int i0, i1;
+    if (c < nj) { i0 = d.j_i0[(size_t)w * nj + c]; i1 = d.j_i1[(size_t)w * nj + c]; }
+    else { i0 = __ldg(c_i0 + c - nj); i1 = __ldg(c_i1 + c - nj); }
+    lev[c] = (unsigned short)(i0 + 1);
+    lstage[c] = (unsigned short)(i1 + 1);
+  }
   if (rm > 1) {
     // pos[c] = 1: contact c may extend the run of contact c - 1: same ordered body pair and bit-identical
     // normal (one manifold, or one body's ground contacts), so the two share the contact frame
@@ -97,9 +106,7 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
   if (lane == 0) {
     int pl = 0, pp = 0, plen = 0;
     for (int c = 0; c < nc; c++) {
-      int i0, i1;
-      if (c < nj) { i0 = d.j_i0[(size_t)w * nj + c]; i1 = d.j_i1[(size_t)w * nj + c]; }
-      else { i0 = __ldg(c_i0 + c - nj); i1 = __ldg(c_i1 + c - nj); }
+      const int i0 = (int)lev[c] - 1, i1 = (int)lstage[c] - 1;
       if (rm > 1 && pos[c] != 0 && plen < rm) {                         // extends the previous run
         pos[c - 1] &= 0x7fff;                                            // the previous block is no longer the last
         lev[c] = (unsigned short)pl;
@@ -726,6 +733,27 @@ size_t egg_stream_smem(const EggDev& d) {
   return m > sched ? m : sched;
 }
 
+template <int NT>
+cudaError_t launch_records_nt(const EggDev& d, double dt, int G, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (e != cudaSuccess) return e;
+  egg_records_kernel<NT><<<d.W, NT, smem, s>>>(d, dt, G);
+  return cudaGetLastError();
+}
+// Threads per world by the constraints a world typically has (joints + a few contacts per body), not
+// by its capacity.  Measured (131072 x legged20, ~43 constraints): 3.8 ms at 256 threads, 1.8 at 64,
+// 1.6 at 32; 16384 x pile64 (~410): 1.41 ms at 256, 1.24 at 128, 1.27 at 64.
+cudaError_t launch_records(const EggDev& d, double dt, int G, size_t smem, cudaStream_t s) {
+  static const int env_nt = env_i("EGG_RECORDS_NT", 0);
+  const int est = d.nj + 6 * d.n;
+  const int nt = env_nt ? env_nt : (est <= 192 ? 32 : (est <= 768 ? 128 : 256));
+  if (nt <= 32) return launch_records_nt<32>(d, dt, G, smem, s);
+  if (nt <= 64) return launch_records_nt<64>(d, dt, G, smem, s);
+  if (nt <= 128) return launch_records_nt<128>(d, dt, G, smem, s);
+  return launch_records_nt<256>(d, dt, G, smem, s);
+}
+
 // Group-stream assembly: schedule (per world) -> rounds (per group) -> records (per world).
 cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t s) {
   const int G = 32 / d.lpw;
@@ -744,16 +772,7 @@ cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t 
   const int ngroups = (d.W + G - 1) / G;
   egg_rounds_kernel<<<(ngroups + 3) / 4, 128, 0, s>>>(d, G);
   const size_t smem = (size_t)(EGG_DYN + EGG_STAT + 6) * d.n * sizeof(double);
-  if (d.nrec <= 128) {
-    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (e != cudaSuccess) return e;
-    egg_records_kernel<64><<<d.W, 64, smem, s>>>(d, dt, G);
-  } else {
-    if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_records_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (e != cudaSuccess) return e;
-    egg_records_kernel<256><<<d.W, 256, smem, s>>>(d, dt, G);
-  }
-  return cudaGetLastError();
+  return launch_records(d, dt, G, smem, s);
 }
 
 cudaError_t egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s) {
