@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fixed-k", action="store_true", help="skip the extra fixed-K (K = 20) measurement of the c3 workload")
+    ap.add_argument("--no-evolving", action="store_true", help="skip the extra evolving-state measurement (the batch stepped on without restore)")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="32 = opt-in FP32 constraint records (not the headline)")
     return ap.parse_args()
 
@@ -313,6 +314,27 @@ def run_ours(args):
 
     dense_flops = float(b.dense_work().sum()) if dense else None
 
+    # ---- evolving state: the same batch stepped on from the timed state WITHOUT restore, so the scene
+    # relaxes / spreads as it would in a rollout (the headline restores the same start state before
+    # every step: fixed work per step, the worst case for the contact-rich pile) ----
+    evolving = None
+    if horizon == 1 and not args.no_evolving:
+        b.restore()
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(stream)
+        b.step(dt, n_steps=args.steps)
+        h1.record(stream)
+        barrier()
+        t4 = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        st4 = b.status()
+        evolving = {"value": W * world * args.steps / (float(t4.item()) * 1e-3), "unit": "world-steps/s", "steps": args.steps,
+                    "ms_per_step": float(t4.item()) / max(args.steps, 1), "mean_contacts_last_step": float(st4["n_contacts"].mean()),
+                    "mean_sweeps_last_step": float(st4["sweeps"].mean()), "status_or": int(np.bitwise_or.reduce(st4["status"])),
+                    "what": "the timed state stepped on without restore (contacts and sweeps change from step to step)"}
+
     # ---- fixed-K line (reference termination AND fixed-K throughput): the same workload
     # with the sweep count pinned to K = 20; parity at the same K: test_pgs_fixed_k20_stepwise ----
     fixed_k = None
@@ -451,6 +473,8 @@ def run_ours(args):
                     "steps": args.e2e_steps, "api": "egg_set_state + egg_step + egg_get_bodies (pinned host buffers)"},
             "gpu_launches": int(launches),
         }
+        if evolving is not None:
+            line["evolving"] = evolving
         if fixed_k is not None:
             line["fixed_k"] = fixed_k
         if strong is not None:

@@ -184,7 +184,7 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
   // The PGS solver streams group-interleaved records (format 1, egg_pgs_stream.cu); the dense path,
   // Jacobi / SOR and the relaxation read per-world 240-byte records (format 0, egg_pgs.cu).
   d.rec_fmt = (dsc->solver == EGG_SOLVER_PGS) ? 1 : 0;
-  d.rmax = 1;
+  d.rmax = 0;
   // the group-stream assembly keeps u16 level tables of 2 (n + 4 nrec) bytes per world in shared memory
   if (d.rec_fmt && d.nrec > 24000) { g_err = "PGS: more than 24000 constraint slots per world (n_joints + max_contacts) are not supported"; egg_destroy(b); return EGG_ERR_UNSUPPORTED; }
   if (d.rec_fmt) {

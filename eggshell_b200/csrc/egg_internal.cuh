@@ -81,7 +81,7 @@ struct EggDev {
   // group-stream assembly of the default PGS variant (egg_pgs_stream.cu)
   int blkb;                   // stream bytes per block: 32 (multipliers) + 208 (FP64 record) or 112 (precision = 32 record)
   int lpw;                    // lanes per world = stage cap; G = 32 / lpw worlds share a warp and a record stream
-  int rmax;                   // 1: one block per lane and stage (egg_pgs_stream.cu); > 1: a lane carries a run of up to rmax
+  int rmax;                   // 0: one block per lane and stage (egg_pgs_stream.cu); >= 1: run format, a lane carries a run of up to rmax
                               //    consecutive blocks on the same body pair through a stage (egg_pgs_runs.cu)
   unsigned* st_runs;          // [W][nrec] run lengths of a world's stage, 4 bits per lane of the world (run format only, else null)
   int run_cap;                // runs per world and stage of the run format (<= lpw; bounded by the staging buffer)

@@ -642,7 +642,7 @@ cudaError_t launch_lpw(const EggDev& d, double dt, cudaStream_t s) {
 int egg_runs_rmax(const EggDev& d) {
   static const int env_runs = env_i("EGG_PGS_RUNS", -1);   // development override of EGG_OPT_PGS_RUNS (quirks bit 16)
   const bool want = env_runs >= 0 ? env_runs != 0 : (d.prm.quirks & 16) != 0;
-  if (!want || !d.rec_fmt || !d.st_runs || d.iso < 1 || d.lpw > 8 || d.blkb != RECB64 + LAMB) return 1;
+  if (!want || !d.rec_fmt || !d.st_runs || d.iso < 1 || d.lpw > 8 || d.blkb != RECB64 + LAMB) return 0;
   return RUN_MAX;
 }
 

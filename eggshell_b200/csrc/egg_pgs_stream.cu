@@ -55,7 +55,7 @@ namespace {
 // Assembly 1/3: dependency levels and stages of one world (one warp per world, lane 0 scans).
 //   level(c) = 1 + max level of earlier constraints sharing a body  (constraints in reference
 //   order: joints, then contacts, ensembles.cc:234-239); a level is cut into stages of <= cap.
-// rm > 1 (egg_pgs_runs.cu): the unit is a RUN of up to rm consecutive constraints on the same
+// rm > 0 (egg_pgs_runs.cu): the unit is a RUN of up to rm consecutive constraints on the same
 //   ordered body pair (the contacts of one manifold, ensembles.cc:449-473): they would occupy
 //   consecutive levels anyway, and one lane can carry both bodies' accumulators through them.
 // Out: c_pos[c] = stage << 8 | lane << 3 | index inside the run, st_cnt[stage] (rm == 1) or
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
   const size_t per = (size_t)(n + 4 * nrec + 2 + 7) & ~(size_t)7;
   unsigned short* blast = reinterpret_cast<unsigned short*>(sm_raw) + (size_t)wl * per;
   unsigned short* lev = blast + n;
-  unsigned short* pos = lev + nrec;     // unit index inside its level (bits 0..11 when rm > 1: | k << 12 | last-of-run << 15)
+  unsigned short* pos = lev + nrec;     // unit index inside its level (bits 0..11 when rm > 0: | k << 12 | last-of-run << 15)
   unsigned short* lcnt = pos + nrec;
   unsigned short* lstage = lcnt + nrec + 1;
   if (wl >= wpc || w >= d.W) return;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
     lev[c] = (unsigned short)(i0 + 1);
     lstage[c] = (unsigned short)(i1 + 1);
   }
-  if (rm > 1) {
+  if (rm > 0) {
     // pos[c] = 1: contact c may extend the run of contact c - 1: same ordered body pair and bit-identical
     // normal (one manifold, or one body's ground contacts), so the two share the contact frame
     const double* gm = d.c_geom + (size_t)w * 7 * d.maxc;
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
     int pl = 0, pp = 0, plen = 0;
     for (int c = 0; c < nc; c++) {
       const int i0 = (int)lev[c] - 1, i1 = (int)lstage[c] - 1;
-      if (rm > 1 && pos[c] != 0 && plen < rm) {                         // extends the previous run
+      if (rm > 0 && pos[c] != 0 && plen < rm) {                         // extends the previous run
         pos[c - 1] &= 0x7fff;                                            // the previous block is no longer the last
         lev[c] = (unsigned short)pl;
         pos[c] = (unsigned short)(pp | (plen << 12) | 0x8000);
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
       if (i1 >= 0) blast[i1] = (unsigned short)(l + 1);
       lev[c] = (unsigned short)l;
       pp = lcnt[l]++;
-      pos[c] = (unsigned short)((rm > 1) ? (pp | 0x8000) : pp);
+      pos[c] = (unsigned short)((rm > 0) ? (pp | 0x8000) : pp);
       pl = l; plen = 1;
       nl = max(nl, l + 1);
     }
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(128) egg_schedule_kernel(EggDev d, int cap, in
   ns = __shfl_sync(0xffffffffu, ns, 0);
   __syncwarp();
   int* cp = d.c_pos + (size_t)w * nrec;
-  if (rm > 1) {
+  if (rm > 0) {
     unsigned* sr = d.st_runs + (size_t)w * nrec;
     for (int t = lane; t < ns; t += 32) sr[t] = 0u;
     __syncwarp();
@@ -766,9 +766,9 @@ cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t 
     const size_t smem = wpc * per;
     if (smem > 48 * 1024) EGG_FIRST(e, cudaFuncSetAttribute(egg_schedule_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (e != cudaSuccess) return e;
-    egg_schedule_kernel<<<(d.W + wpc - 1) / wpc, 128, smem, s>>>(d, d.rmax > 1 ? egg_run_cap(d) : d.lpw, wpc, d.rmax);
+    egg_schedule_kernel<<<(d.W + wpc - 1) / wpc, 128, smem, s>>>(d, d.rmax > 0 ? egg_run_cap(d) : d.lpw, wpc, d.rmax);
   }
-  if (d.rmax > 1) return egg_launch_assemble_runs_tail(d, dt, s);   // run headers and run-format records (egg_pgs_runs.cu)
+  if (d.rmax > 0) return egg_launch_assemble_runs_tail(d, dt, s);   // run headers and run-format records (egg_pgs_runs.cu)
   const int ngroups = (d.W + G - 1) / G;
   egg_rounds_kernel<<<(ngroups + 3) / 4, 128, 0, s>>>(d, G);
   const size_t smem = (size_t)(EGG_DYN + EGG_STAT + 6) * d.n * sizeof(double);
@@ -776,7 +776,7 @@ cudaError_t egg_launch_assemble_stream(const EggDev& d, double dt, cudaStream_t 
 }
 
 cudaError_t egg_launch_solve_pgs_stream(const EggDev& d, double dt, cudaStream_t s) {
-  if (d.rmax > 1) return egg_launch_solve_pgs_runs(d, dt, s);
+  if (d.rmax > 0) return egg_launch_solve_pgs_runs(d, dt, s);
   if (d.iso == 2) return launch_nbuf<12, 2>(d, dt, s);
   if (d.iso == 1) return launch_nbuf<12, 1>(d, dt, s);
   return launch_nbuf<8, 0>(d, dt, s);

@@ -147,48 +147,52 @@ __host__ __device__ inline unsigned nib_ge(unsigned x, int v) {
   else m = b2 | b3;
   return m & 0x11111111u;
 }
-// Fused integrate of world w from its accumulator sb [n][6] (a = M^-1 J^T x), `lanes` lanes of the
-// warp starting at lane `sl` stride over the bodies:
+// Fused integrate of body b of one world (dyn [18][n], stat [16][n]) with its accumulator
+// a = M^-1 J^T x = (al, aa):  v' = v + dt (M^-1 f + a); p += dt (v+v')/2; R <- WtoQ((w+w')/2, dt) R
+// (ensembles.cc:535,572-591).  Returns true when the new state is not finite.
+__device__ __forceinline__ bool stream_integrate_body(double* dyn, const double* st, int n, int b, double alx, double aly, double alz, double aax, double aay, double aaz, double dt) {
+  const double mi = __ldg(st + b);
+  double Ii[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) Ii[c] = __ldg(st + (1 + c) * n + b);
+  d3 fl = mk3(st[10 * n + b], st[11 * n + b], st[12 * n + b]);
+  d3 ft = mk3(st[13 * n + b], st[14 * n + b], st[15 * n + b]);
+  d3 v = mk3(dyn[12 * n + b], dyn[13 * n + b], dyn[14 * n + b]);
+  d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
+  d3 vn = v + dt * (fl * mi + mk3(alx, aly, alz));
+  d3 wn = wv + dt * (mmulv(Ii, ft) + mk3(aax, aay, aaz));
+  d3 vmid = (v + vn) / 2.0, wmid = (wv + wn) / 2.0;
+  d3 p = mk3(dyn[b], dyn[n + b], dyn[2 * n + b]) + dt * vmid;
+  double z2 = dot3(wmid, wmid);
+  d3 axis = (z2 > 0) ? wmid / sqrt(z2) : wmid;
+  double ha = 0.5 * (norm3(wmid) * dt);
+  double qw = cos(ha), sn = sin(ha);
+  double qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
+  double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  double Q[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
+  double R[9], Rn[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) R[c] = dyn[(3 + c) * n + b];
+  mmulm(Q, R, Rn);
+  dyn[b] = p.x; dyn[n + b] = p.y; dyn[2 * n + b] = p.z;
+#pragma unroll
+  for (int c = 0; c < 9; c++) dyn[(3 + c) * n + b] = Rn[c];
+  dyn[12 * n + b] = vn.x; dyn[13 * n + b] = vn.y; dyn[14 * n + b] = vn.z;
+  dyn[15 * n + b] = wn.x; dyn[16 * n + b] = wn.y; dyn[17 * n + b] = wn.z;
+  double chk = p.x + p.y + p.z + vn.x + vn.y + vn.z + wn.x + wn.y + wn.z;
+  return !(fabs(chk) < 1e300);
+}
+// The same for world w from its accumulator sb [n][6]; `lanes` lanes of the warp starting at lane
+// `sl` stride over the bodies.
 __device__ __forceinline__ void stream_integrate_world(const EggDev& d, int w, const double* sb, int sl, int lanes, double dt) {
   const int n = d.n;
-  const int LPW = lanes;
-  // v' = v + dt (M^-1 f + a); p += dt (v+v')/2; R <- WtoQ((w+w')/2, dt) R  (ensembles.cc:535,572-591)
   double* dyn = d.dyn + (size_t)w * EGG_DYN * n;
   const double* st = d.stat + (size_t)w * EGG_STAT * n;
   bool bad = false;
-  for (int b = sl; b < n; b += LPW) {
+  for (int b = sl; b < n; b += lanes) {
     const double* q = sb + b * 6;
-    const double mi = __ldg(st + b);
-    double Ii[9];
-#pragma unroll
-    for (int c = 0; c < 9; c++) Ii[c] = __ldg(st + (1 + c) * n + b);
-    d3 fl = mk3(st[10 * n + b], st[11 * n + b], st[12 * n + b]);
-    d3 ft = mk3(st[13 * n + b], st[14 * n + b], st[15 * n + b]);
-    d3 v = mk3(dyn[12 * n + b], dyn[13 * n + b], dyn[14 * n + b]);
-    d3 wv = mk3(dyn[15 * n + b], dyn[16 * n + b], dyn[17 * n + b]);
-    d3 vn = v + dt * (fl * mi + mk3(q[0], q[1], q[2]));
-    d3 wn = wv + dt * (mmulv(Ii, ft) + mk3(q[3], q[4], q[5]));
-    d3 vmid = (v + vn) / 2.0, wmid = (wv + wn) / 2.0;
-    d3 p = mk3(dyn[b], dyn[n + b], dyn[2 * n + b]) + dt * vmid;
-    double z2 = dot3(wmid, wmid);
-    d3 axis = (z2 > 0) ? wmid / sqrt(z2) : wmid;
-    double ha = 0.5 * (norm3(wmid) * dt);
-    double qw = cos(ha), sn = sin(ha);
-    double qx = sn * axis.x, qy = sn * axis.y, qz = sn * axis.z;
-    double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz, twx = tx * qw, twy = ty * qw, twz = tz * qw;
-    double txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-    double Q[9] = {1 - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1 - (txx + tzz), tyz - twx, txz - twy, tyz + twx, 1 - (txx + tyy)};
-    double R[9], Rn[9];
-#pragma unroll
-    for (int c = 0; c < 9; c++) R[c] = dyn[(3 + c) * n + b];
-    mmulm(Q, R, Rn);
-    dyn[b] = p.x; dyn[n + b] = p.y; dyn[2 * n + b] = p.z;
-#pragma unroll
-    for (int c = 0; c < 9; c++) dyn[(3 + c) * n + b] = Rn[c];
-    dyn[12 * n + b] = vn.x; dyn[13 * n + b] = vn.y; dyn[14 * n + b] = vn.z;
-    dyn[15 * n + b] = wn.x; dyn[16 * n + b] = wn.y; dyn[17 * n + b] = wn.z;
-    double chk = p.x + p.y + p.z + vn.x + vn.y + vn.z + wn.x + wn.y + wn.z;
-    bad |= !(fabs(chk) < 1e300);
+    bad |= stream_integrate_body(dyn, st, n, b, q[0], q[1], q[2], q[3], q[4], q[5], dt);
   }
   if (bad) atomicOr(&d.status[w], 16 /*EGG_ST_NONFINITE*/);
 }
