@@ -344,17 +344,19 @@ def test_pgs_fp32_records_opt_in(name, W, k_max, steps):
     assert worst_all["v"] < 1e-4 and worst_all["w"] < 1e-4
 
 
-@pytest.mark.parametrize("name,W,k_max,lpw", [("stack10", 65536, 10, "1"), ("stack10", 65536, 10, ""), ("pile64", 16384, 5, ""), ("pile64", 8192, 5, "16"), ("legged20", 131072, 10, "")])
-def test_full_size_step_is_bit_reproducible(name, W, k_max, lpw, monkeypatch):
+@pytest.mark.parametrize("name,W,k_max,lpw,opt", [("stack10", 65536, 10, "1", 0), ("stack10", 65536, 10, "", 0), ("pile64", 16384, 5, "", 0), ("pile64", 8192, 5, "16", 0),
+                                                 ("legged20", 131072, 10, "", 0), ("pile64", 16384, 5, "", 16), ("stack10", 65536, 10, "1", 16), ("legged20", 65536, 10, "", 16)])
+def test_full_size_step_is_bit_reproducible(name, W, k_max, lpw, opt, monkeypatch):
     """The kernels are deterministic, so the same full-size step from the same state must give the
     same bits every time.  This is the test that exposes ordering bugs between the shared-memory
     loads of a stage and the TMA copy of the next one (a generic fence instead of the cross-proxy
-    fence made 1-2 % of the worlds differ from run to run at 32 worlds per warp)."""
+    fence made 1-2 % of the worlds differ from run to run at 32 worlds per warp).  The last three
+    cases run the opt-in run format (EGG_OPT_PGS_RUNS), which hands its staging buffer back the same way."""
     import eggshell_b200 as E
     if lpw:
         monkeypatch.setenv("EGG_PGS_LPW", lpw)
     scene = getattr(E.scenes, name)(W)
-    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, max_contacts=1024 if name == "pile64" else 0)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, max_contacts=1024 if name == "pile64" else 0, quirks=E.QUIRKS_REFERENCE | opt)   # opt 16 = the run format
     b.snapshot()
     ref = None
     for r in range(3):

@@ -10,7 +10,7 @@ W = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 k_max = int(sys.argv[3]) if len(sys.argv) > 3 else 50
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 va = sys.argv[5] if len(sys.argv) > 5 else "stream"
-vb = sys.argv[6] if len(sys.argv) > 6 else "fast"
+vb = sys.argv[6] if len(sys.argv) > 6 else "runs"
 fn = {"c2": E.scenes.stack10, "c3": E.scenes.pile64, "c5": E.scenes.legged20}[wl]
 scene = fn(W)
 
@@ -18,11 +18,11 @@ scene = fn(W)
 def run(variant):
     # "stream:1" = variant stream with EGG_PGS_ISO=1 (cap on the isotropic fast-path level)
     name, _, iso = variant.partition(":")
-    os.environ["EGG_PGS_VARIANT"] = name
+    quirks = E.QUIRKS_REFERENCE | (16 if name == "runs" else 0)   # "runs" = EGG_OPT_PGS_RUNS, "stream" = the default kernel
     os.environ.pop("EGG_PGS_ISO", None)
     if iso:
         os.environ["EGG_PGS_ISO"] = iso
-    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, taps=True, max_contacts=1024 if wl == "c3" else 0)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, taps=True, max_contacts=1024 if wl == "c3" else 0, quirks=quirks)
     out = []
     for s in range(steps):
         b.step(scene["dt"])
