@@ -28,12 +28,33 @@ def _stepwise(scene, nsteps, worlds_idx, batch_kw, oracle_kw, tol=1e-9, lam_tol=
             os_ = ows[k].stats()
             assert st["sweeps"][wi] == os_["sweeps"], f"step {s} world {wi}: sweeps {st['sweeps'][wi]} != {os_['sweeps']}"
             lam, rhs, rs = ows[k].solution()
-            con_rs = b.contacts()["row_state"][wi, :len(rs)]
+            con = b.contacts()
+            con_rs = con["row_state"][wi, :len(rs)]
             assert np.array_equal(con_rs, rs), f"step {s} world {wi}: row clamp states differ"
+            # Near-tie probe: the CUDA kernels contract multiply-adds, the oracle does not, so equal clamp
+            # states only mean something if no free multiplier sits within rounding distance of a bound.
+            # margin = distance of the closest strictly-inside multiplier to its bound (friction rows
+            # [-1, 1], normal rows [0, inf)); it must dwarf the CUDA-vs-oracle difference of that world.
+            lam = np.asarray(lam); rs = np.asarray(rs)
+            # bounded rows: contact blocks, except the first contact block after joints (quirk q2: block c is
+            # projected with the bounds of block c - 1, sparse_iterations_utils.cc:169,180,229-235)
+            blk = np.arange(len(lam)) // 3
+            bounded = (blk > scene["nj"]) if scene["nj"] else np.ones(len(lam), dtype=bool)
+            free = (rs == 0) & bounded
+            if free.any() and os_["sweeps"] > 0:      # zero sweeps: x is the unprojected initial guess (= rhs)
+                row = np.arange(len(lam)) % 3
+                dist = np.where(row < 2, 1.0 - np.abs(lam), np.abs(lam))[free]
+                diff = float(np.max(np.abs(con["lam"][wi, :len(lam)] - lam)))
+                margin = float(dist.min())
+                worst_all["clamp_margin"] = min(worst_all.get("clamp_margin", np.inf), margin)
+                worst_all["clamp_margin_over_diff"] = min(worst_all.get("clamp_margin_over_diff", np.inf), margin / max(diff, 1e-300))
         assert worst["lam"] <= lam_tol, f"lambda mismatch {worst['lam']:.3e}"
         for k_, v_ in worst.items():
             worst_all[k_] = max(worst_all.get(k_, 0.0), v_)
     b.close()
+    if "clamp_margin_over_diff" in worst_all:
+        # a free multiplier closer to its bound than ~the rounding difference would make the clamp state a coin toss
+        assert worst_all["clamp_margin_over_diff"] > 10.0, f"near-tie: margin {worst_all['clamp_margin']:.3e} is within 10x of the CUDA-vs-oracle difference"
     return worst_all
 
 
