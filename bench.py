@@ -46,7 +46,7 @@ SETTLE = {"c4": 4}            # steps taken from the scene's start state before 
 DENSE = {"c4"}                # workloads on the reference's default dense solver (solver 0); the others use PGS (solver 1)
 FIXED_K = 20
 FLOPS_PER_ROW_UPDATE = 54.0
-ROW_STREAM_BYTES = 240.0      # one row streamed from HBM
+ROW_STREAM_BYTES = 208.0      # bytes of one 3-row block streamed from HBM per Gauss-Seidel pass: 176 B record + 32 B multipliers
 
 
 def parse():
@@ -396,8 +396,8 @@ def run_ours(args):
         bytes_step = E.scenes.algorithmic_bytes_per_world_step(n, nj)
         nc_mean = rows_last / W / 3.0
         # Dominant kernel = PGS solve + fused integrate (egg_pgs_stream_kernel).  Gauss-Seidel visits
-        # every 3-row block once per pass; SURVEY.md §8(d): 240 B per block streamed from HBM
-        # (208 B record + 32 B multipliers), and the multipliers go back (32 B) after every sweep.
+        # every 3-row block once per pass: 208 B per block streamed from HBM (176 B record + 32 B
+        # multipliers), and the multipliers go back (32 B) after every sweep.
         # Passes per world = sweeps + 2 (x0 scatter and the final read-only residual pass; probe
         # chunks, round headers and extra exact-residual passes are NOT counted: a lower bound).
         blocks_w = st["n_rows"].astype(np.float64) / 3.0
@@ -448,7 +448,7 @@ def run_ours(args):
         # efficiency of the kernel on the traffic it chose to generate (every block streamed once per pass)
         roof_stream = None if dense else {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                        "stream_bytes_per_launch": solve_bytes, "stream_over_algorithmic": solve_bytes / algo_bytes,
-                       "definition": "NOT the roofline: DRAM efficiency on the kernel's own record stream, W*B_step + sum_worlds blocks*((sweeps+2)*240 + sweeps*32) bytes"}
+                       "definition": "NOT the roofline: DRAM efficiency on the kernel's own record stream, W*B_step + sum_worlds blocks*((sweeps+2)*208 + sweeps*32) bytes (FP64 records)"}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             from oracle import pyoracle as O

@@ -79,7 +79,7 @@ struct EggDev {
   int* iso_flag;              // [1] device: 1 while every body seen by egg_init was isotropic
   int iso;                    // host copy of iso_flag, valid after the first step following egg_init
   // group-stream assembly of the default PGS variant (egg_pgs_stream.cu)
-  int blkb;                   // stream bytes per block: 32 (multipliers) + 208 (FP64 record) or 112 (precision = 32 record)
+  int blkb;                   // stream bytes per block: 32 (multipliers) + 176 (FP64 record) or 112 (precision = 32 record)
   int lpw;                    // lanes per world = stage cap; G = 32 / lpw worlds share a warp and a record stream
   int rmax;                   // 0: one block per lane and stage (egg_pgs_stream.cu); >= 1: run format, a lane carries a run of up to rmax
                               //    consecutive blocks on the same body pair through a stage (egg_pgs_runs.cu)

@@ -4,7 +4,8 @@
 // (profiles/r1i_pgs_stream_final_summary.txt, per-line stall samples): a warp-stage of ~2200
 // cycles of which the block arithmetic is ~570; header decode, guards, prefetch cursor, copy issue
 // and the wait for the copy are paid per STAGE, and the stage count is the dependency depth of the
-// world (pile64: 121 levels for 495 blocks).  And 272 stream bytes per block pass, 72 of them a
+// world (pile64: 121 levels for 495 blocks).  And 272 stream bytes per block pass (then; 240 since the
+// third frame row is rebuilt and the packed word travels with the multipliers), 72 of them a
 // contact frame that the contacts of one manifold share.
 //
 // Here the unit of scheduling is a RUN: up to RUN_MAX consecutive contacts of the reference order

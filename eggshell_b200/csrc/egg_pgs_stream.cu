@@ -37,8 +37,8 @@
 //     one is a cross-proxy fence (fence.proxy.async.shared::cta), see the comment at the fence.
 //   * World groups are handed out by an atomic counter.
 //
-// Per warp: 64 B + G x n x 48 B accumulators + 64 B + G x LPW x 240 B staging.  64-body worlds:
-// 20096 B -> 11 resident warps of 4 worlds per SM at 168 registers.
+// Per warp: 64 B + G x n x 48 B accumulators + 64 B + G x LPW x 208 B staging.  64-body worlds:
+// 19072 B -> 11 resident warps of 4 worlds per SM at 164 registers.
 //
 // Replaces: sparse::GaussSeidelIteration + GetResidualError + the velocity/position update, i.e.
 // /root/reference/eggshell/sparse_iterations.cc:148-226,51-69,
@@ -246,17 +246,18 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : 4) egg_records_kernel(Eg
     const unsigned total = gs[ro + G];
     double2* lam = reinterpret_cast<double2*>(gs + ro + HDRB + (size_t)LAMB * (start + idx));
     lam[0] = make_double2(v[REC_RHS], v[REC_RHS + 1]);              // x0 = rhs
-    lam[1] = make_double2(v[REC_RHS + 2], 0.0);
+    lam[1] = make_double2(v[REC_RHS + 2], __longlong_as_double((long long)pk));
     const int recb = d.blkb - LAMB;
     unsigned char* rp = gs + ro + HDRB + (size_t)LAMB * total + (size_t)recb * (start + idx);
     if (recb == RECB64) {
       double o[SREC];
 #pragma unroll
-      for (int q = 0; q < 18; q++) o[q] = v[q];                     // Rc, r0, r1, D off-diagonal
+      for (int q = 0; q < 6; q++) o[q] = v[q];                      // rows 0 and 1 of Rc (row 2 = +-(row 0 x row 1))
 #pragma unroll
-      for (int q = 0; q < 3; q++) { o[18 + q] = v[REC_INVA + q]; o[21 + q] = v[REC_RHS + q]; }
-      o[24] = __longlong_as_double((long long)pk);
-      o[25] = 0.0;
+      for (int q = 0; q < 9; q++) o[6 + q] = v[9 + q];              // r0, r1, D off-diagonal
+#pragma unroll
+      for (int q = 0; q < 3; q++) { o[15 + q] = v[REC_INVA + q]; o[18 + q] = v[REC_RHS + q]; }
+      o[21] = 0.0;
       double2* out = reinterpret_cast<double2*>(rp);
 #pragma unroll
       for (int q = 0; q < SREC / 2; q++) out[q] = make_double2(o[2 * q], o[2 * q + 1]);
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
   extern __shared__ __align__(128) unsigned char smraw[];
   const int n = d.n, lane = threadIdx.x, sub = lane / LPW, sl = lane % LPW;
   // shared memory: [mbarrier probes 8 B][mbarrier rounds, buffer 0, 8 B][dummy body 48 B: the ground / world
-  //                anchor, always zero][G x n x 6 doubles accumulators][64 B header + G x LPW x (32 + 208) B staging]
+  //                anchor, always zero][G x n x 6 doubles accumulators][64 B header + G x LPW x (32 + 176) B staging]
   const unsigned bar2 = s32(smraw), bar = s32(smraw + 8);
   double* sb = reinterpret_cast<double*>(smraw + 64) + (size_t)sub * 6 * n;
   const int dummy = -(sub * n) - 1;            // body index of the dummy relative to this world's sb
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
 
     // One block on record v.  MODE_INIT: a = M^-1 J^T x0 (x0 = rhs, already in the record);
     // MODE_UPDATE: projected row-by-row update + impulse scatter; MODE_RESID: residual terms only.
-    auto step = [&](const double2* v, double x0, double x1, double x2, int mode, bool mine, unsigned lam_off, unsigned round_off, int round_meta, bool finalize) {
+    auto step = [&](const double2* v, double x0, double x1, double x2, unsigned long long pk_lam, int mode, bool mine, unsigned lam_off, unsigned round_off, int round_meta, bool finalize) {
       if (!mine) return;
       double fld[24];
       unsigned long long pk;
@@ -383,8 +384,15 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         pk = (unsigned long long)__double_as_longlong(v[6].x);
       } else {
 #pragma unroll
-        for (int q = 0; q < 12; q++) { fld[2 * q] = v[q].x; fld[2 * q + 1] = v[q].y; }
-        pk = (unsigned long long)__double_as_longlong(v[12].x);
+        for (int q = 0; q < 3; q++) { fld[2 * q] = v[q].x; fld[2 * q + 1] = v[q].y; }                  // Rc rows 0, 1
+#pragma unroll
+        for (int q = 3; q < 11; q++) { fld[3 + 2 * q] = v[q].x; if (q < 10) fld[4 + 2 * q] = v[q].y; }   // r0 .. rhs -> fld[9..23]
+        pk = pk_lam;
+        // row 2 of the frame: a rotation's third row is row 0 x row 1; a joint's frame is -I (det -1)
+        const double sg = ((int)(pk >> 21) < nj) ? -1.0 : 1.0;
+        fld[6] = sg * (fld[1] * fld[5] - fld[2] * fld[4]);
+        fld[7] = sg * (fld[2] * fld[3] - fld[0] * fld[5]);
+        fld[8] = sg * (fld[0] * fld[4] - fld[1] * fld[3]);
       }
       const int i0 = (int)(pk & 1023u) - 1, i1 = (int)((pk >> 10) & 1023u) - 1;
       // range guard: a record that is not a record must never become an address (three compares per
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
         double n2 = x2 + ((e2 - DO1 * d0) - DO2 * d1) * IA2;
         n2 = (n2 < lo2) ? lo2 : n2;
         d2 = n2 - x2;
-        st_sector(reinterpret_cast<double*>(gs + lam_off), n0, n1, n2, 0.0);
+        st_sector(reinterpret_cast<double*>(gs + lam_off), n0, n1, n2, __longlong_as_double((long long)pk_lam));
       }
       // impulse scatter: a += M^-1 J^T delta
       const double ix = RC0 * d0 + RC3 * d1 + RC6 * d2, iy = RC1 * d0 + RC4 * d1 + RC7 * d2, iz = RC2 * d0 + RC5 * d1 + RC8 * d2;
@@ -533,11 +541,13 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
           const int cur_meta = probe ? probe_meta : (start | (total << 8) | (cnt << 16));
           if (phase == PH_INIT && t == 0) { probe_off = 0; probe_meta = cur_meta; probe_cnt = cnt; }   // first probe: the world's stage 0
           double x0 = 0, x1 = 0, x2 = 0;
+          unsigned long long pk_lam = 0ull;       // the block's packed word travels in the 4th slot of its multiplier sector
           if (mine) {
             const double2* lq = reinterpret_cast<const double2*>(stage + HDRB) + (start + sl) * 2;
             const double2* sp = reinterpret_cast<const double2*>(stage + HDRB + (probe ? 32 : total) * LAMB) + (start + sl) * SPIECES;
             const double2 la = lq[0], lb = lq[1];
             x0 = la.x; x1 = la.y; x2 = lb.x;
+            pk_lam = (unsigned long long)__double_as_longlong(lb.y);
 #pragma unroll
             for (int p = 0; p < SPIECES; p++) buf[p] = sp[p];
           }
@@ -575,7 +585,7 @@ __global__ void __launch_bounds__(32, MINB) egg_pgs_stream_kernel(EggDev d, doub
               }
             }
           }
-          step(buf, x0, x1, x2, mode, mine, cur_off + HDRB + (unsigned)(((cur_meta & 255) + sl) * LAMB), cur_off, cur_meta, !probe);
+          step(buf, x0, x1, x2, pk_lam, mode, mine, cur_off + HDRB + (unsigned)(((cur_meta & 255) + sl) * LAMB), cur_off, cur_meta, !probe);
           __syncwarp();                            // accumulator writes visible to the next round
           roff = roff_next;
         }
@@ -659,7 +669,7 @@ int env_i(const char* name, int dflt) {
 template <bool F32>
 size_t stream_smem(const EggDev& d, int lpw) {
   const int G = 32 / lpw;
-  return 64 + (size_t)G * 48 * d.n + (size_t)(HDRB + 32 * ((F32 ? RECB32 : RECB64) + LAMB));   // FP64, 64 bodies: 20096 B, 11 CTAs per SM
+  return 64 + (size_t)G * 48 * d.n + (size_t)(HDRB + 32 * ((F32 ? RECB32 : RECB64) + LAMB));   // FP64, 64 bodies: 19072 B, 11 CTAs per SM
 }
 
 template <int LPW, int MINB, int ISO, bool F32>

@@ -7,11 +7,11 @@
 namespace {
 
 #define kInf CUDART_INF
-// Two record formats (layouts below): FP64 records of 26 doubles = 208 B = 13 x 16 B, and the opt-in
+// Two record formats (layouts below): FP64 records of 22 doubles = 176 B = 11 x 16 B, and the opt-in
 // precision = 32 format of 24 floats + the packed word = 112 B = 7 x 16 B (both odd multiples of
 // 16 B: conflict-free 128-bit shared-memory reads at these strides).
-constexpr int SREC = 26;            // doubles per FP64 stream record
-constexpr int RECB64 = SREC * 8;    // 208
+constexpr int SREC = 22;            // doubles per FP64 stream record
+constexpr int RECB64 = SREC * 8;    // 176
 constexpr int RECB32 = 112;
 constexpr int LAMB = 32;            // bytes of one block's multipliers (3 doubles + pad = one sector)
 constexpr int BLKB_MAX = RECB64 + LAMB;   // stream bytes per block, FP64 records (allocation bound)
@@ -60,16 +60,19 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       : "memory");
 }
 
-// Stream record (26 doubles): [0..8] Rc, [9..11] r0, [12..14] r1, [15..17] D off-diagonal,
-// [18..20] 1/(D+cfm), [21..23] rhs, [24] packed (i0+1 | (i1+1) << 10 | kind << 20 | original
-// constraint index << 21), [25] spare.  The multipliers are NOT in the record: a round keeps them
-// in one contiguous array of 32-byte sectors in front of its records, so that the write-back of
-// a warp-stage is a run of consecutive full sectors.  (With the multipliers inside each record
-// the scattered 32-byte stores alone cost 40 % of the stream: tools/micro/stream_bench measures
-// 4.1 TB/s with them against 6.2 read-only and 5.6 with the compact array; and partial-sector
-// stores additionally made L2 fetch every sector it merged: +8 GB reads per launch, profiles/r1f.)
-// precision = 32 record (112 B): the same 24 numbers as floats (96 B), then the packed word and 8
-// spare bytes.  The kernel widens them to double as it reads; multipliers, accumulators and all
+// Stream record (22 doubles): [0..5] rows 0 and 1 of Rc, [6..8] r0, [9..11] r1, [12..14] D
+// off-diagonal, [15..17] 1/(D+cfm), [18..20] rhs, [21] spare.  Row 2 of the frame is NOT stored:
+// Rc is a rotation (or -I for a joint), so row 2 = +-(row 0 x row 1), three multiply-subtracts off
+// the dependent chain instead of 24 bytes per block pass.  The multipliers are NOT in the record
+// either: a round keeps them in one contiguous array of 32-byte sectors in front of its records
+// (x0 x1 x2 | packed word: i0+1 | (i1+1) << 10 | kind << 20 | original constraint index << 21), so
+// that the write-back of a warp-stage is a run of consecutive full sectors.  (With the multipliers
+// inside each record the scattered 32-byte stores alone cost 40 % of the stream:
+// tools/micro/stream_bench measures 4.1 TB/s with them against 6.2 read-only and 5.6 with the
+// compact array; and partial-sector stores additionally made L2 fetch every sector it merged:
+// +8 GB reads per launch, profiles/r1f.)
+// precision = 32 record (112 B): all 24 numbers (the full frame) as floats (96 B), then the packed
+// word and 8 spare bytes.  The kernel widens them to double as it reads; multipliers, accumulators and all
 // arithmetic stay FP64.
 // Inside the kernel the 24 numbers of either format are fld[0..23]:
 #define RC0 fld[0]
