@@ -197,7 +197,8 @@ int egg_create(const egg_desc* dsc, egg_batch** out) {
     DA(d.st_cnt, (size_t)W * d.nrec);
     // run format (egg_pgs_runs.cu): FP64 records, at most 8 lanes per world; whether the bodies are
     // isotropic (its other condition) is known after egg_init, so the choice is made at the first step
-    if (dsc->precision == 64 && d.lpw <= 8) {
+    const bool runs_asked = (dsc->quirks & EGG_OPT_PGS_RUNS) != 0 || (getenv("EGG_PGS_RUNS") && atoi(getenv("EGG_PGS_RUNS")) != 0);
+    if (runs_asked && dsc->precision == 64 && d.lpw <= 8) {   // [W][nrec] words: only for batches that asked for the run format
       DA(d.st_runs, (size_t)W * d.nrec);
       d.run_cap = egg_run_cap(d);
     }

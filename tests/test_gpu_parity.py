@@ -826,3 +826,74 @@ def test_init_stabilize_matches_oracle():
     steps, e2 = b.init_stabilize()
     assert np.all((e2 <= 1e-9) | (steps == 100)) and np.all(steps > 0)
     b.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Edge cases: empty and ragged inputs, capacity limits, API errors.
+def test_edge_cases_empty_ragged_capacity_and_errors():
+    """(1) Worlds without any constraint (free fall): no contacts, zero sweeps / pivots, state equal to
+    the oracle's, both solvers.  (2) A ragged batch: worlds with and without contacts share a warp
+    group, W is neither a multiple of the worlds per warp nor of 32; one world of one body.
+    (3) Contact capacity: a world with more contacts than max_contacts drops the tail and says so
+    (EGG_ST_CONTACT_OVERFLOW), the other worlds of the batch are untouched.  (4) Call-order and
+    argument errors come back as error codes, never as a crash."""
+    import eggshell_b200 as E
+    from eggshell_b200.batch import EggError
+    # (1) free fall, PGS and dense
+    scene = E.scenes.cairn(5, rocks=3, zb=(5.0, 8.0), seed=41)
+    scene["p"][:, :, 0] = 2.0 * np.arange(3)                            # apart from each other and far above the ground
+    for kw, okw, fn in ((dict(solver=E.SOLVER_PGS), dict(solver=1), _stepwise),):
+        worst = fn(scene, 3, list(range(5)), kw, okw)
+        print("free fall pgs", worst)
+    _stepwise_dense(scene, 3, list(range(5)))
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, taps=True)
+    b.step(scene["dt"], n_steps=2)
+    st = b.status()
+    assert int(st["n_contacts"].max()) == 0 and int(st["sweeps"].max()) == 0 and int(st["status"].max()) == 0
+    b.close()
+    # (2) ragged: 7 worlds, worlds 2 and 5 lifted far above everything (no contacts), the others collide
+    scene = E.scenes.cairn(7, rocks=5, zb=(0.1, 0.6), seed=43)
+    for wq in (2, 5):
+        scene["p"][wq, :, 2] += 50.0
+        scene["p"][wq, :, 0] += 3.0 * np.arange(5)
+    worst = _stepwise(scene, 6, list(range(7)), dict(solver=E.SOLVER_PGS), dict(solver=1))
+    print("ragged worst", worst)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS)
+    b.step(scene["dt"])
+    cnt = b.status()["n_contacts"]
+    assert cnt[2] == 0 and cnt[5] == 0 and (np.delete(cnt, [2, 5]) > 0).all()
+    b.close()
+    _stepwise_dense(scene, 4, list(range(7)))
+    one = E.scenes.cairn(1, rocks=1, zb=(0.05, 0.1), seed=44)          # one world, one body touching the ground
+    worst = _stepwise(one, 5, [0], dict(solver=E.SOLVER_PGS), dict(solver=1))
+    print("one body worst", worst)
+    # (3) capacity: pile64 has ~500 contacts per world; with room for 64 the tail is dropped and flagged
+    scene = E.scenes.pile64(3)
+    scene["p"][1, :, 2] += 50.0                                         # world 1: no contacts at all
+    scene["p"][1, :, 0] += 3.0 * np.arange(64)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=10, max_contacts=64)
+    b.step(scene["dt"])
+    st = b.status()
+    assert (st["status"][[0, 2]] & 8).all() and st["status"][1] == 0, st["status"]
+    assert (st["n_contacts"][[0, 2]] == 64).all() and st["n_contacts"][1] == 0
+    p, R, v, w = b.bodies()
+    assert np.isfinite(p).all() and np.isfinite(v).all()
+    b.close()
+    # (4) errors
+    b = E.Batch(2, 3, 0, solver=E.SOLVER_PGS)
+    with pytest.raises(EggError):
+        b.step(0.01)                                                    # egg_step before egg_init: EGG_ERR_STATE
+    b.close()
+    scene = E.scenes.cairn(2, rocks=2, seed=45)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS)
+    with pytest.raises(EggError):
+        b.step(-1.0)                                                    # dt <= 0: EGG_ERR_ARG
+    with pytest.raises(EggError):
+        b.step(0.01, integrator=0)                                      # EXPLICIT_EULER: unsupported, as the reference refuses it with contacts
+    b.step(0.01)                                                        # the batch is still usable
+    assert int(b.status()["status"].max()) == 0
+    b.close()
+    with pytest.raises(EggError):
+        E.Batch(0, 3, 0)                                                # no worlds
+    with pytest.raises(EggError):
+        E.Batch(2, 3, 0, solver=E.SOLVER_DENSE_MURTY, precision=32)     # FP32 records exist for PGS only
