@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU-baseline sample time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fixed-k", action="store_true", help="skip the extra fixed-K (K = 20) measurement of the c3 workload")
+    ap.add_argument("--no-fixed-k", action="store_true", help="skip the extra fixed-K (K = 20) measurement of the PGS workloads (and the strong-scaling extra of c3)")
     ap.add_argument("--no-evolving", action="store_true", help="skip the extra evolving-state measurement (the batch stepped on without restore)")
     ap.add_argument("--precision", type=int, default=64, choices=[64, 32], help="32 = opt-in FP32 constraint records (not the headline)")
     return ap.parse_args()
@@ -338,20 +338,24 @@ def run_ours(args):
     # ---- fixed-K line (reference termination AND fixed-K throughput): the same workload
     # with the sweep count pinned to K = 20; parity at the same K: test_pgs_fixed_k20_stepwise ----
     fixed_k = None
-    if args.workload == "c3" and args.k_max != FIXED_K and not args.no_fixed_k:
+    if not dense and args.k_max != FIXED_K and not args.no_fixed_k:
         b.close()
         b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=FIXED_K, max_contacts=maxc, device=local, precision=args.precision)
         b.set_stream(stream.cuda_stream)
         b.snapshot()
         for _ in range(3):
-            b.restore(); b.step(dt)
+            b.restore(); b.step(dt, n_steps=horizon)
         b.sync()
         b.set_profiling(True); b.kernel_ms()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(stream)
         for _ in range(args.steps):
-            b.restore(); b.step(dt)
+            b.restore(); b.step(dt, n_steps=horizon)
+            if horizon > 1:                  # MPC: one cost kernel + one allgather per horizon, as in the headline
+                b.rollout_costs(costs.data_ptr())
+                if world > 1:
+                    dist.all_gather_into_tensor(all_costs, costs)
         g1.record(stream)
         barrier()
         t3 = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
@@ -360,7 +364,7 @@ def run_ours(args):
         k3 = b.kernel_ms()
         b.set_profiling(False)
         st3 = b.status()
-        fixed_k = {"k": FIXED_K, "value": W * world * args.steps / (float(t3.item()) * 1e-3), "unit": "world-steps/s",
+        fixed_k = {"k": FIXED_K, "value": W * world * args.steps * horizon / (float(t3.item()) * 1e-3), "unit": "world-steps/s",
                    "ms_per_step": float(t3.item()) / max(args.steps, 1), "mean_sweeps": float(st3["sweeps"].mean()),
                    "kernel_ms_per_step": {"narrowphase": k3[0] / max(k3[3], 1.0), "assembly": k3[1] / max(k3[3], 1.0), "solve_integrate": k3[2] / max(k3[3], 1.0)},
                    "status_or": int(np.bitwise_or.reduce(st3["status"])), "parity": "tests/test_gpu_parity.py::test_pgs_fixed_k20_stepwise"}
