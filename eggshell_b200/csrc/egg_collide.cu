@@ -183,8 +183,9 @@ __device__ int clip_polygon(const double* px, const double* py, int np, double n
   return m;
 }
 
-// collision.cc:273-388 (everything after the 15 axis tests).  out: [k][7] = pos, normal, depth.
-__device__ int manifold(const BoxD& box1, const BoxD& box2, const Sat& s, int* code_out, double* out) {
+// collision.cc:273-388 (everything after the 15 axis tests).  out: [k][4] = pos, depth; every contact of
+// a manifold carries the same normal (*nrm_out), so the per-thread contact buffer holds it once.
+__device__ int manifold(const BoxD& box1, const BoxD& box2, const Sat& s, int* code_out, double* out, d3* nrm_out) {
   const double kTolerance = 1e-9;
   const double* R1 = box1.R;
   const double* R2 = box2.R;
@@ -204,8 +205,8 @@ __device__ int manifold(const BoxD& box1, const BoxD& box2, const Sat& s, int* c
     line_closest_approach(pa, ua, pb, ub, &alpha, &beta);
     d3 pos = (pa + ua * alpha + pb + ub * beta) * 0.5;
     out[0] = pos.x; out[1] = pos.y; out[2] = pos.z;
-    out[3] = aEE.x; out[4] = aEE.y; out[5] = aEE.z;
-    out[6] = -s.mEE;
+    out[3] = -s.mEE;
+    *nrm_out = aEE;
     return 1;
   }
   *code_out = s.cFN;
@@ -261,20 +262,19 @@ __device__ int manifold(const BoxD& box1, const BoxD& box2, const Sat& s, int* c
     d3 pos = Rc + Rx * fx[i] + Ry * fy[i];
     double depth = -(dot3(Aface_normal, pos) + Ad);
     if ((fabs(depth) > kTolerance || s.aacount >= 2) && cnt < EGG_MAX_PAIR_CONTACTS) {
-      double* o = out + 7 * cnt;
+      double* o = out + 4 * cnt;
       o[0] = pos.x; o[1] = pos.y; o[2] = pos.z;
-      o[3] = s.aFN.x; o[4] = s.aFN.y; o[5] = s.aFN.z;
-      o[6] = depth;
+      o[3] = depth;
       cnt++;
     }
   }
   if (cnt == 0) {
     out[0] = box2.c.x; out[1] = box2.c.y; out[2] = box2.c.z;
-    out[3] = s.aFN.x; out[4] = s.aFN.y; out[5] = s.aFN.z;
-    out[6] = -s.mFN;
+    out[3] = -s.mFN;
     *code_out = 16;
     cnt = 1;
   }
+  *nrm_out = s.aFN;
   return cnt;
 }
 
@@ -303,8 +303,8 @@ __device__ int block_excl_scan(int v, int* total, int* wsum) {
 
 __device__ inline void pair_from_index(int q, int n, int* pi, int* pj) {
   // q = i (2n - i - 1)/2 + (j - i - 1)
-  double tn = 2.0 * n - 1.0;
-  int i = (int)floor((tn - sqrt(tn * tn - 8.0 * q)) * 0.5);
+  const float tn = 2.0f * (float)n - 1.0f;           // a float estimate is enough: the two loops below make it exact
+  int i = (int)floorf((tn - sqrtf(tn * tn - 8.0f * (float)q)) * 0.5f);
   if (i < 0) i = 0;
   while (i > 0 && (i * (2 * n - i - 1)) / 2 > q) i--;
   while (((i + 1) * (2 * n - i - 2)) / 2 <= q) i++;
@@ -473,7 +473,8 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
   const double* jc = d.jc + (size_t)w * 6 * nj;
   for (int h0 = 0; h0 < nhits; h0 += NT) {
     const int h = h0 + tid;
-    double cb[7 * EGG_MAX_PAIR_CONTACTS];
+    double cb[4 * EGG_MAX_PAIR_CONTACTS];     // pos, depth per contact
+    d3 cn = mk3(0, 0, 0);                      // the manifold's normal
     int cnt = 0, rawcnt = 0, code = 0, bi = 0, bj = 0;
     if (h < nhits) {
       const int q = hitlist[h];
@@ -487,13 +488,14 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
         const double depth = (r1 + r2) - dist;
         const d3 nn = (dist > 0) ? dc / dist : mk3(0, 0, 1);
         const d3 pos = b1.c + nn * (r1 - depth * 0.5);
-        cb[0] = pos.x; cb[1] = pos.y; cb[2] = pos.z; cb[3] = nn.x; cb[4] = nn.y; cb[5] = nn.z; cb[6] = depth;
+        cb[0] = pos.x; cb[1] = pos.y; cb[2] = pos.z; cb[3] = depth;
+        cn = nn;
         code = 17;
         rawcnt = 1;
       } else {
         Sat s;
         sat_test(b1, b2, s);
-        rawcnt = manifold(b1, b2, s, &code, cb);
+        rawcnt = manifold(b1, b2, s, &code, cb, &cn);
       }
       if (d.pair_code) { d.pair_code[(size_t)w * P + q] = (unsigned char)code; d.pair_cnt[(size_t)w * P + q] = (unsigned char)rawcnt; }
       // CheckAndCorrectEnsembleState, restricted to this body pair (ensembles.cc:264-313):
@@ -511,20 +513,20 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
         d3 p1 = B1.c + mmulv(B1.R, cbv);
         d3 jp = (p0 + p1) / 2.0;
         for (int c = 0; c < rawcnt; c++) {
-          d3 cp = mk3(cb[7 * c], cb[7 * c + 1], cb[7 * c + 2]);
+          d3 cp = mk3(cb[4 * c], cb[4 * c + 1], cb[4 * c + 2]);
           if (closer_than(jp - cp, dmin)) del |= 1u << c;
         }
       }
       for (int a = 0; a < rawcnt; a++)
         for (int b = a + 1; b < rawcnt; b++) {
-          d3 pa = mk3(cb[7 * a], cb[7 * a + 1], cb[7 * a + 2]);
-          d3 pb = mk3(cb[7 * b], cb[7 * b + 1], cb[7 * b + 2]);
+          d3 pa = mk3(cb[4 * a], cb[4 * a + 1], cb[4 * a + 2]);
+          d3 pb = mk3(cb[4 * b], cb[4 * b + 1], cb[4 * b + 2]);
           if (closer_than(pa - pb, dmin)) del |= 1u << b;
         }
       for (int c = 0; c < rawcnt; c++)
         if (!(del & (1u << c))) {
           if (cnt != c)
-            for (int k = 0; k < 7; k++) cb[7 * cnt + k] = cb[7 * c + k];
+            for (int k = 0; k < 4; k++) cb[4 * cnt + k] = cb[4 * c + k];
           cnt++;
         }
     }
@@ -535,8 +537,9 @@ __global__ void __launch_bounds__(NT) egg_collide_kernel(EggDev d) {
     for (int c = 0; c < cnt; c++, slot++) {
       if (slot >= maxc) continue;
       c_i0[slot] = bi; c_i1[slot] = bj; c_code[slot] = code;
-#pragma unroll
-      for (int k = 0; k < 7; k++) geom[k * maxc + slot] = cb[7 * c + k];
+      geom[0 * maxc + slot] = cb[4 * c]; geom[1 * maxc + slot] = cb[4 * c + 1]; geom[2 * maxc + slot] = cb[4 * c + 2];
+      geom[3 * maxc + slot] = cn.x; geom[4 * maxc + slot] = cn.y; geom[5 * maxc + slot] = cn.z;
+      geom[6 * maxc + slot] = cb[4 * c + 3];
     }
     base += tot;
     raw += rtot;
