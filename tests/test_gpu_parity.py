@@ -897,3 +897,40 @@ def test_edge_cases_empty_ragged_capacity_and_errors():
         E.Batch(0, 3, 0)                                                # no worlds
     with pytest.raises(EggError):
         E.Batch(2, 3, 0, solver=E.SOLVER_DENSE_MURTY, precision=32)     # FP32 records exist for PGS only
+
+
+@pytest.mark.parametrize("name,W,k_max", [("pile64", 16384, 5), ("stack10", 65536, 10), ("legged20", 131072, 10)])
+def test_full_size_worlds_are_independent_of_the_batch(name, W, k_max):
+    """Size-independent property that ties the full-size batches to the oracle-checked small ones: a
+    world's step does not depend on which other worlds share its batch, its warp or its group stream.
+    Sampled worlds of a full-occupancy batch (first / middle / last groups included) are stepped again
+    in a batch of their own -- other lanes per world, other neighbours, other stage cuts -- and must
+    give the same bits; the small batch is then compared with the oracle as usual."""
+    import eggshell_b200 as E
+    scene = getattr(E.scenes, name)(W)
+    maxc = 1024 if name == "pile64" else 0
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=k_max, max_contacts=maxc)
+    b.step(scene["dt"])
+    big = [x.copy() for x in b.bodies()]
+    st_big = b.status()
+    assert int(np.bitwise_or.reduce(st_big["status"])) == 0
+    b.close()
+    pick = np.array([0, 1, 5, W // 3, W // 2 + 3, W - 34, W - 2, W - 1])
+    sub = dict(scene)
+    for key in ("p", "R", "v", "w", "m", "I", "c0", "c1", "f_ext", "shape", "dims"):
+        if key in scene and isinstance(scene[key], np.ndarray) and scene[key].shape[:1] == (W,):
+            sub[key] = scene[key][pick].copy()
+    sub["W"] = len(pick)
+    sb = E.scenes.make_batch(sub, solver=E.SOLVER_PGS, k_max=k_max, max_contacts=maxc, taps=True)
+    ows = [oracle_world(sub, k, solver=1, k_max=k_max)[0] for k in range(len(pick))]
+    sb.step(sub["dt"])
+    for ow in ows:
+        ow.step(sub["dt"])
+    small = sb.bodies()
+    st_small = sb.status()
+    for a, c in zip(small, big):
+        assert np.array_equal(a.view(np.uint64), c[pick].view(np.uint64)), f"{name}: a world's step depends on its batch"
+    assert np.array_equal(st_small["n_contacts"], st_big["n_contacts"][pick]) and np.array_equal(st_small["sweeps"], st_big["sweeps"][pick])
+    worst = compare_step(sb, ows, list(range(len(pick))))
+    print(name, "sampled worlds of the full batch vs oracle", worst)
+    sb.close()
