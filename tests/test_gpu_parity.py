@@ -934,3 +934,45 @@ def test_full_size_worlds_are_independent_of_the_batch(name, W, k_max):
     worst = compare_step(sb, ows, list(range(len(pick))))
     print(name, "sampled worlds of the full batch vs oracle", worst)
     sb.close()
+
+
+def test_full_size_dense_worlds_are_independent_of_the_batch():
+    """The same property on the dense path (persistent CTAs pulling worlds from a queue, per-CTA
+    scratch slabs that are reused from world to world): sampled worlds of a 4096 x chain32 batch,
+    after the settling steps that bring the chain onto the ground, match a batch of their own bit
+    for bit -- state, pivot counts and cfm decisions -- and that batch matches the oracle."""
+    import eggshell_b200 as E
+    W = 4096
+    scene = E.scenes.chain32(W, seed=4000)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_DENSE_MURTY)
+    b.step(scene["dt"], n_steps=3)
+    start = [x.copy() for x in b.bodies()]
+    b.step(scene["dt"])
+    big = [x.copy() for x in b.bodies()]
+    st_big = b.status()
+    assert int(np.bitwise_or.reduce(st_big["status"])) == 0 and int(st_big["pivots"].max()) > 0
+    b.close()
+    pick = np.array([0, 7, W // 2 + 1, W - 300, W - 1])
+    sub = dict(scene)
+    for key in ("p", "R", "v", "w", "m", "I", "c0", "c1"):
+        if key in scene and isinstance(scene[key], np.ndarray) and scene[key].shape[:1] == (W,):
+            sub[key] = scene[key][pick].copy()
+    sub["W"] = len(pick)
+    sb = E.scenes.make_batch(sub, solver=E.SOLVER_DENSE_MURTY, taps=True)
+    sb.set_state(*[x[pick] for x in start])
+    ows = [oracle_world(sub, k, solver=0)[0] for k in range(len(pick))]
+    for k, ow in enumerate(ows):
+        ow.set_state(*[x[pick][k] for x in start])
+    sb.step(sub["dt"])
+    for ow in ows:
+        ow.step(sub["dt"])
+    small = sb.bodies()
+    st_small = sb.status()
+    for a, c in zip(small, big):
+        assert np.array_equal(a.view(np.uint64), c[pick].view(np.uint64)), "dense: a world's step depends on its batch"
+    assert np.array_equal(st_small["pivots"], st_big["pivots"][pick]) and np.array_equal(st_small["cfm_applied"], st_big["cfm_applied"][pick])
+    worst = compare_step(sb, ows, list(range(len(pick))))
+    for k, ow in enumerate(ows):
+        assert st_small["pivots"][k] == ow.stats()["pivots"] and st_small["cfm_applied"][k] == ow.stats()["cfm_applied"]
+    print("dense sampled worlds of the full batch vs oracle", worst, "pivots", st_small["pivots"].tolist())
+    sb.close()
