@@ -976,3 +976,27 @@ def test_full_size_dense_worlds_are_independent_of_the_batch():
         assert st_small["pivots"][k] == ow.stats()["pivots"] and st_small["cfm_applied"][k] == ow.stats()["cfm_applied"]
     print("dense sampled worlds of the full batch vs oracle", worst, "pivots", st_small["pivots"].tolist())
     sb.close()
+
+
+def test_full_size_rollout_is_independent_of_the_batch():
+    """Multi-step form of the property (an MPC horizon): twelve steps of 65536 legged worlds and the
+    same twelve steps of eight of them in a batch of their own end in the same bits."""
+    import eggshell_b200 as E
+    W, steps = 65536, 12
+    scene = E.scenes.legged20(W)
+    b = E.scenes.make_batch(scene, solver=E.SOLVER_PGS, k_max=10)
+    b.step(scene["dt"], n_steps=steps)
+    big = [x.copy() for x in b.bodies()]
+    assert int(np.bitwise_or.reduce(b.status()["status"])) == 0
+    b.close()
+    pick = np.array([0, 3, 9, W // 4, W // 2, W - 40, W - 2, W - 1])
+    sub = dict(scene)
+    for key in ("p", "R", "v", "w", "m", "I", "c0", "c1", "f_ext"):
+        if key in scene and isinstance(scene[key], np.ndarray) and scene[key].shape[:1] == (W,):
+            sub[key] = scene[key][pick].copy()
+    sub["W"] = len(pick)
+    sb = E.scenes.make_batch(sub, solver=E.SOLVER_PGS, k_max=10)
+    sb.step(sub["dt"], n_steps=steps)
+    for a, c in zip(sb.bodies(), big):
+        assert np.array_equal(a.view(np.uint64), c[pick].view(np.uint64)), "rollout: a world's trajectory depends on its batch"
+    sb.close()
