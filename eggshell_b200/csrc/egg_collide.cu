@@ -287,6 +287,10 @@ __device__ int block_excl_scan(int v, int* total, int* wsum) {
     int t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
+  if (NT == 32) {     // one warp per world: the warp scan is the block scan (no barrier, no shared memory)
+    *total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+  }
   __syncthreads();   // protects wsum reuse across consecutive calls
   if (lane == 31) wsum[wid] = inc;
   __syncthreads();
